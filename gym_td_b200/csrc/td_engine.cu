@@ -1,0 +1,568 @@
+// td_engine.cu -- C-ABI entry points (include/td_b200.h) over the kernels in td_kernels.cuh.
+// Host logic only: buffer layout, validation, launches on the caller's stream, error reporting.
+// There is no CPU fallback: every compute entry point needs a CUDA device.
+#include "td_kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace td;
+
+struct td_handle {
+    int device, kind, L, cells, cells_pad, n_envs;
+    int n_maps, map_stride, difficulty;
+    int record_bytes, map_bytes, smem_per_warp, scratch_off;
+    uint8_t *records;
+    uint8_t *maps;
+    uint32_t *mt;
+    EnvStats *stats;
+    td_stats *stats_dev;
+    bool opponent_seeded;
+    long long steps;
+    td_config cfg;
+    std::string err;
+};
+
+static std::string g_create_error;
+
+static int fail(td_handle *h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define TD_CUDA(h, call)                                                                         \
+    do {                                                                                         \
+        cudaError_t e_ = (call);                                                                 \
+        if (e_ != cudaSuccess)                                                                   \
+            return fail((h), TD_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+static int round16(int x) { return (x + 15) & ~15; }
+
+extern "C" int td_abi_version(void) { return TD_ABI_VERSION; }
+
+extern "C" const char *td_last_error(const td_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+// gym_TD/envs/TDParam.py:1-94, 105-111
+extern "C" void td_default_config(td_config *c)
+{
+    static const double eLP[4][2] = {{820, 1700}, {2050, 3000}, {6000, 8000}, {8000, 12000}};
+    static const double espd[4][2] = {{.25, .25}, {.13, .13}, {.1, .1}, {.1, .1}};
+    static const double edef[4][2] = {{0, 0}, {200, 250}, {600, 800}, {80, 100}};
+    static const double ecost[4][2] = {{8, 8}, {15, 15}, {40, 40}, {30, 30}};
+    static const double tatk[4][2] = {{454, 540}, {651, 771}, {566, 691}, {358, 424}};
+    static const int trge[4][2] = {{3, 3}, {2, 2}, {4, 4}, {3, 3}};
+    static const int tspl[4][2] = {{0, 0}, {0, 0}, {1, 1}, {0, 0}};
+    static const double tcost[4][2] = {{10, 10}, {17, 17}, {23, 23}, {12, 12}};
+    static const double tintv[4][2] = {{2, 2}, {4, 4}, {7, 7}, {4.75, 4.75}};
+    memset(c, 0, sizeof(*c));
+    for (int t = 0; t < TD_NTYPES; ++t)
+        for (int l = 0; l < TD_NLV; ++l) {
+            c->enemy_LP[t][l] = eLP[t][l];
+            c->enemy_speed[t][l] = espd[t][l];
+            c->enemy_defense[t][l] = edef[t][l];
+            c->enemy_cost[t][l] = ecost[t][l];
+            c->tower_attack[t][l] = tatk[t][l];
+            c->tower_range[t][l] = trge[t][l];
+            c->tower_splash_range[t][l] = tspl[t][l];
+            c->tower_cost[t][l] = tcost[t][l];
+            c->tower_attack_interval[t][l] = tintv[t][l];
+        }
+    c->tower_destruct_return = .5;
+    c->frozen_time = 2;
+    c->frozen_ratio = .2;
+    c->attacker_init_cost = 0;
+    c->defender_init_cost = 10;
+    c->base_LP = 5;
+    c->max_cost = 100;
+    c->reward_kill = 0.1;
+    c->penalty_leak = 10.;
+    c->reward_time = 0.001;
+    c->attacker_cost_init_rate = .5;
+    c->attacker_cost_final_rate = 1;
+    c->defender_cost_rate = .2;
+    c->tower_distance = 2;
+    c->enemy_upgrade_at = 0.75;
+    c->attacker_action_interval = 1;
+    c->defender_action_interval = 1;
+    c->max_episode_steps = 1200;
+    c->max_tower_lv = 1;
+}
+
+static int validate_config(td_handle *h, const td_config *c)
+{
+    if (!c) return fail(h, TD_E_INVALID, "config is NULL");
+    if (c->max_tower_lv != 1) return fail(h, TD_E_INVALID, "this build supports max_tower_lv == 1 only");
+    if (c->tower_distance < 0 || c->tower_distance > 8) return fail(h, TD_E_INVALID, "tower_distance out of range [0, 8]");
+    if (c->max_episode_steps < 1) return fail(h, TD_E_INVALID, "max_episode_steps < 1");
+    if (c->base_LP > 0x7fff) return fail(h, TD_E_INVALID, "base_LP too large");
+    if (c->attacker_action_interval < 0 || c->attacker_action_interval > 0x7fff ||
+        c->defender_action_interval < 0 || c->defender_action_interval > 0x7fff)
+        return fail(h, TD_E_INVALID, "action interval out of range");
+    if (c->frozen_time < 0 || c->frozen_time > 255) return fail(h, TD_E_INVALID, "frozen_time out of range [0, 255]");
+    for (int t = 0; t < TD_NTYPES; ++t)
+        for (int l = 0; l < TD_NLV; ++l)
+            if (c->tower_range[t][l] < 0 || c->tower_splash_range[t][l] < 0 || !(c->enemy_LP[t][l] > 0))
+                return fail(h, TD_E_INVALID, "negative range or non-positive enemy LP in config tables");
+    return TD_OK;
+}
+
+static int upload_config(td_handle *h, const td_config *c)
+{
+    DevConfig d;
+    memset(&d, 0, sizeof(d));
+    for (int t = 0; t < TD_NTYPES; ++t)
+        for (int l = 0; l < TD_NLV; ++l) {
+            d.enemy_LP[t][l] = c->enemy_LP[t][l];
+            d.enemy_speed[t][l] = c->enemy_speed[t][l];
+            d.enemy_defense[t][l] = c->enemy_defense[t][l];
+            d.enemy_cost[t][l] = c->enemy_cost[t][l];
+            d.tower_attack[t][l] = c->tower_attack[t][l];
+            d.tower_cost[t][l] = c->tower_cost[t][l];
+            d.tower_range[t][l] = c->tower_range[t][l];
+            d.tower_splash[t][l] = c->tower_splash_range[t][l];
+        }
+    for (int t = 0; t < TD_NTYPES; ++t) {
+        // TDElements.py:152-170 passes (.., tower_cost, tower_attack_interval) into lvup(.., intv, cost):
+        // after LvUp the interval is tower_cost[t][1] and Tower.cost grows by tower_attack_interval[t][1].
+        d.tower_intv[t][0] = c->tower_attack_interval[t][0];
+        d.tower_intv[t][1] = c->tower_cost[t][1];
+        d.tower_refund[t][0] = c->tower_cost[t][0];
+        volatile double grown = c->tower_cost[t][0] + c->tower_attack_interval[t][1];
+        d.tower_refund[t][1] = grown;
+    }
+    d.destruct_return = c->tower_destruct_return;
+    d.frozen_ratio = c->frozen_ratio;
+    d.atk_init_cost = c->attacker_init_cost;
+    d.def_init_cost = c->defender_init_cost;
+    d.max_cost = c->max_cost;
+    d.reward_kill = c->reward_kill;
+    d.penalty_leak = c->penalty_leak;
+    d.reward_time = c->reward_time;
+    d.rate_init = c->attacker_cost_init_rate;
+    d.rate_final = c->attacker_cost_final_rate;
+    d.def_rate = c->defender_cost_rate;
+    d.upgrade_at = c->enemy_upgrade_at;
+    d.frozen_time = c->frozen_time;
+    d.base_LP = c->base_LP < 0 ? -1 : c->base_LP;
+    d.tower_distance = c->tower_distance;
+    d.atk_interval = c->attacker_action_interval;
+    d.def_interval = c->defender_action_interval;
+    d.max_steps = c->max_episode_steps;
+    TD_CUDA(h, cudaMemcpyToSymbol(cc, &d, sizeof(d)));
+    h->cfg = *c;
+    return TD_OK;
+}
+
+static void fill_params(const td_handle *h, StepParams &p)
+{
+    memset(&p, 0, sizeof(p));
+    p.records = h->records;
+    p.maps = h->maps;
+    p.mt = h->mt;
+    p.stats = h->stats;
+    p.n_envs = h->n_envs;
+    p.n_maps = h->n_maps;
+    p.map_stride = h->map_stride;
+    p.L = h->L;
+    p.cells = h->cells;
+    p.cells_pad = h->cells_pad;
+    p.record_bytes = h->record_bytes;
+    p.map_bytes = h->map_bytes;
+    p.smem_per_warp = h->smem_per_warp;
+    p.scratch_off = h->scratch_off;
+    p.difficulty = h->difficulty;
+    p.opponent_seeded = h->opponent_seeded ? 1 : 0;
+}
+
+static int grid_of(const td_handle *h) { return (h->n_envs + kWarpsPerCta - 1) / kWarpsPerCta; }
+static size_t smem_of(const td_handle *h) { return (size_t)kWarpsPerCta * h->smem_per_warp; }
+
+template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
+{
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+}
+
+extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n_envs, int device, td_handle **out)
+{
+    if (!out) return fail(nullptr, TD_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (env_kind < TD_KIND_DEF || env_kind > TD_KIND_2P) return fail(nullptr, TD_E_INVALID, "unknown env kind");
+    if (map_size < 4 || map_size > TD_MAX_L) return fail(nullptr, TD_E_INVALID, "map_size must be in [4, 64]");
+    if (n_envs < 1) return fail(nullptr, TD_E_INVALID, "n_envs < 1");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, TD_E_CUDA, std::string("no CUDA device available (") +
+                    (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + "); there is no CPU fallback");
+    if (device < 0 || device >= count) return fail(nullptr, TD_E_INVALID, "device index out of range");
+    td_handle *h = new (std::nothrow) td_handle();
+    if (!h) return fail(nullptr, TD_E_ALLOC, "out of host memory");
+    h->device = device; h->kind = env_kind; h->L = map_size; h->cells = map_size * map_size;
+    h->cells_pad = round16(h->cells); h->n_envs = n_envs;
+    h->n_maps = 0; h->map_stride = n_envs; h->difficulty = 1;
+    h->record_bytes = kOffMap6 + h->cells_pad;
+    h->map_bytes = kMapHdrBytes + 2 * h->cells_pad;
+    h->scratch_off = h->record_bytes + h->map_bytes;
+    int scratch = std::max(768, std::max(h->cells_pad, round16(2 * std::min(h->cells, 6 * map_size))));
+    h->smem_per_warp = h->scratch_off + scratch;
+    h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
+    h->opponent_seeded = false; h->steps = 0;
+    td_config def;
+    if (!cfg) { td_default_config(&def); cfg = &def; }
+    int rc = validate_config(h, cfg);
+    auto bail = [&](int code) { g_create_error = h->err; td_destroy(h); return code; };
+    if (rc != TD_OK) return bail(rc);
+    if ((e = cudaSetDevice(device)) != cudaSuccess) { h->err = cudaGetErrorString(e); return bail(TD_E_CUDA); }
+    size_t smem = smem_of(h);
+    if (smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
+    if ((e = allow_smem(td_step_kernel<TD_KIND_DEF, false>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_step_kernel<TD_KIND_DEF, true>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_step_kernel<TD_KIND_ATK, false>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_step_kernel<TD_KIND_2P, false>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_step_kernel<TD_KIND_2P, true>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
+        (e = allow_smem(td_observe_kernel, smem)) != cudaSuccess) {
+        h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+        return bail(TD_E_CUDA);
+    }
+    size_t rec_total = (size_t)n_envs * h->record_bytes;
+    if ((e = cudaMalloc(&h->records, rec_total)) != cudaSuccess ||
+        (e = cudaMemset(h->records, 0, rec_total)) != cudaSuccess ||
+        (e = cudaMalloc(&h->stats, (size_t)n_envs * sizeof(EnvStats))) != cudaSuccess ||
+        (e = cudaMemset(h->stats, 0, (size_t)n_envs * sizeof(EnvStats))) != cudaSuccess ||
+        (e = cudaMalloc(&h->stats_dev, sizeof(td_stats))) != cudaSuccess) {
+        h->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
+        return bail(TD_E_ALLOC);
+    }
+    rc = upload_config(h, cfg);
+    if (rc != TD_OK) return bail(rc);
+    *out = h;
+    return TD_OK;
+}
+
+extern "C" int td_destroy(td_handle *h)
+{
+    if (!h) return TD_OK;
+    if (h->records) cudaFree(h->records);
+    if (h->maps) cudaFree(h->maps);
+    if (h->mt) cudaFree(h->mt);
+    if (h->stats) cudaFree(h->stats);
+    if (h->stats_dev) cudaFree(h->stats_dev);
+    delete h;
+    return TD_OK;
+}
+
+extern "C" int td_set_config(td_handle *h, const td_config *cfg)
+{
+    if (!h) return TD_E_INVALID;
+    int rc = validate_config(h, cfg);
+    if (rc != TD_OK) return rc;
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaDeviceSynchronize());
+    return upload_config(h, cfg);
+}
+
+extern "C" int td_get_layout(const td_handle *h, td_layout *out)
+{
+    if (!h || !out) return TD_E_INVALID;
+    out->record_bytes = h->record_bytes;
+    out->off_header = 0;
+    out->off_towers = kOffTowers;
+    out->off_enemies = kOffEnemies;
+    out->off_map6 = kOffMap6;
+    out->tower_stride = kTowerBytes;
+    out->enemy_stride = kEnemyBytes;
+    out->cap_towers = TD_CAP_TOWERS;
+    out->cap_enemies = TD_CAP_ENEMIES;
+    out->map_record_bytes = h->map_bytes;
+    out->mt_words = kMtWords;
+    out->pad_ = 0;
+    return TD_OK;
+}
+
+extern "C" int td_upload_maps(td_handle *h, const td_map *maps, int n_maps)
+{
+    if (!h) return TD_E_INVALID;
+    if (!maps || n_maps < 1) return fail(h, TD_E_INVALID, "td_upload_maps: no maps");
+    std::vector<uint8_t> pool((size_t)n_maps * h->map_bytes, 0);
+    for (int i = 0; i < n_maps; ++i) {
+        const td_map &m = maps[i];
+        if (m.map_size != h->L) return fail(h, TD_E_INVALID, "td_upload_maps: map_size differs from the handle's");
+        if (m.num_roads < 1 || m.num_roads > TD_ROADS) return fail(h, TD_E_INVALID, "td_upload_maps: num_roads out of range");
+        if (m.max_dist < 0 || m.max_dist > 254) return fail(h, TD_E_INVALID, "td_upload_maps: road too long");
+        uint8_t *rec = pool.data() + (size_t)i * h->map_bytes;
+        MapHdr hd;
+        memset(&hd, 0, sizeof(hd));
+        for (int r = 0; r < TD_ROADS; ++r) {
+            int s = r < m.num_roads ? m.start[r] : 0;
+            if (s < 0 || s >= h->cells) return fail(h, TD_E_INVALID, "td_upload_maps: start cell out of range");
+            hd.start[r] = (uint16_t)s;
+        }
+        if (m.end < 0 || m.end >= h->cells) return fail(h, TD_E_INVALID, "td_upload_maps: end cell out of range");
+        hd.end = (uint16_t)m.end;
+        hd.num_roads = (uint8_t)m.num_roads;
+        hd.maxd_p1 = (uint8_t)(m.max_dist + 1);
+        memcpy(rec, &hd, sizeof(hd));
+        memcpy(rec + kMapHdrBytes, m.cells, (size_t)h->cells);
+        memcpy(rec + kMapHdrBytes + h->cells_pad, m.dist, (size_t)h->cells);
+        // every road cell must lead somewhere inside the board (guards the on-device walk)
+        for (int c = 0; c < h->cells; ++c) {
+            if (!(m.cells[c] & 1) || c == m.end) continue;
+            int d = (m.cells[c] >> 4) & 3, r = c / h->L, col = c % h->L;
+            int nr = r + (d == 2) - (d == 3), nc = col + (d == 0) - (d == 1);
+            if (nr < 0 || nr >= h->L || nc < 0 || nc >= h->L || !(m.cells[nr * h->L + nc] & 1))
+                return fail(h, TD_E_INVALID, "td_upload_maps: a road cell points off the road");
+        }
+    }
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaDeviceSynchronize());
+    if (h->maps) { cudaFree(h->maps); h->maps = nullptr; }
+    TD_CUDA(h, cudaMalloc(&h->maps, pool.size()));
+    TD_CUDA(h, cudaMemcpy(h->maps, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+    h->n_maps = n_maps;
+    return TD_OK;
+}
+
+extern "C" int td_set_map_stride(td_handle *h, int stride)
+{
+    if (!h) return TD_E_INVALID;
+    if (stride < 0) return fail(h, TD_E_INVALID, "stride < 0");
+    h->map_stride = stride;
+    return TD_OK;
+}
+
+extern "C" int td_set_difficulty(td_handle *h, int difficulty)
+{
+    if (!h) return TD_E_INVALID;
+    if (difficulty < 0 || difficulty > 1) return fail(h, TD_E_INVALID, "on-device scripted opponents exist for difficulty 0 and 1");
+    h->difficulty = difficulty;
+    return TD_OK;
+}
+
+extern "C" int td_reset(td_handle *h, const uint8_t *mask_dev, const int32_t *map_ids_dev, float *obs_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (h->n_maps < 1) return fail(h, TD_E_STATE, "td_reset: upload maps first");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    td_reset_kernel<<<grid_of(h), kWarpsPerCta * 32, smem_of(h), (cudaStream_t)stream>>>(p, mask_dev, map_ids_dev, obs_dev);
+    TD_CUDA(h, cudaGetLastError());
+    return TD_OK;
+}
+
+__global__ void td_rng_pos_kernel(uint8_t *records, int record_bytes, int first, int n, const int32_t *pos, int32_t *pos_out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    td_env_header *h = reinterpret_cast<td_env_header *>(records + (size_t)(first + i) * record_bytes);
+    if (pos) h->rng_pos = pos[i];
+    if (pos_out) pos_out[i] = h->rng_pos;
+}
+
+extern "C" int td_seed_opponent(td_handle *h, const uint32_t *states, int first_env, int n)
+{
+    if (!h) return TD_E_INVALID;
+    if (!states || first_env < 0 || n < 1 || first_env + n > h->n_envs) return fail(h, TD_E_INVALID, "td_seed_opponent: bad range");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaDeviceSynchronize());
+    if (!h->mt) {
+        TD_CUDA(h, cudaMalloc(&h->mt, (size_t)h->n_envs * kMtWords * sizeof(uint32_t)));
+        TD_CUDA(h, cudaMemset(h->mt, 0, (size_t)h->n_envs * kMtWords * sizeof(uint32_t)));
+    }
+    std::vector<uint32_t> words((size_t)n * kMtWords);
+    std::vector<int32_t> pos((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        memcpy(&words[(size_t)i * kMtWords], states + (size_t)i * (kMtWords + 1), kMtWords * sizeof(uint32_t));
+        uint32_t p = states[(size_t)i * (kMtWords + 1) + kMtWords];
+        if (p > (uint32_t)kMtWords) return fail(h, TD_E_INVALID, "td_seed_opponent: position > 624");
+        pos[(size_t)i] = (int32_t)p;
+    }
+    int32_t *pos_dev = nullptr;
+    TD_CUDA(h, cudaMalloc(&pos_dev, (size_t)n * sizeof(int32_t)));
+    cudaError_t e = cudaMemcpy(pos_dev, pos.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(h->mt + (size_t)first_env * kMtWords, words.data(), words.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        td_rng_pos_kernel<<<(n + 255) / 256, 256>>>(h->records, h->record_bytes, first_env, n, pos_dev, nullptr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(pos_dev);
+    if (e != cudaSuccess) return fail(h, TD_E_CUDA, std::string("td_seed_opponent: ") + cudaGetErrorString(e));
+    h->opponent_seeded = true;
+    return TD_OK;
+}
+
+extern "C" int td_get_opponent(td_handle *h, int first_env, int n, uint32_t *states)
+{
+    if (!h) return TD_E_INVALID;
+    if (!states || first_env < 0 || n < 1 || first_env + n > h->n_envs) return fail(h, TD_E_INVALID, "td_get_opponent: bad range");
+    if (!h->mt) return fail(h, TD_E_STATE, "td_get_opponent: generators were never seeded");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaDeviceSynchronize());
+    std::vector<uint32_t> words((size_t)n * kMtWords);
+    std::vector<int32_t> pos((size_t)n);
+    int32_t *pos_dev = nullptr;
+    TD_CUDA(h, cudaMalloc(&pos_dev, (size_t)n * sizeof(int32_t)));
+    td_rng_pos_kernel<<<(n + 255) / 256, 256>>>(h->records, h->record_bytes, first_env, n, nullptr, pos_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy(pos.data(), pos_dev, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(words.data(), h->mt + (size_t)first_env * kMtWords, words.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaFree(pos_dev);
+    if (e != cudaSuccess) return fail(h, TD_E_CUDA, std::string("td_get_opponent: ") + cudaGetErrorString(e));
+    for (int i = 0; i < n; ++i) {
+        memcpy(states + (size_t)i * (kMtWords + 1), &words[(size_t)i * kMtWords], kMtWords * sizeof(uint32_t));
+        states[(size_t)i * (kMtWords + 1) + kMtWords] = (uint32_t)pos[(size_t)i];
+    }
+    return TD_OK;
+}
+
+static int check_io(td_handle *h, const td_step_io *io)
+{
+    if (!io) return fail(h, TD_E_INVALID, "td_step: io is NULL");
+    if (h->n_maps < 1) return fail(h, TD_E_STATE, "td_step: upload maps and reset first");
+    if (h->kind != TD_KIND_ATK && !io->def_action_dev) return fail(h, TD_E_INVALID, "td_step: def_action_dev is required");
+    if (h->kind != TD_KIND_DEF && !io->atk_action_dev) return fail(h, TD_E_INVALID, "td_step: atk_action_dev is required");
+    if (h->kind == TD_KIND_ATK && io->multi_action) return fail(h, TD_E_INVALID, "td_step: multi_action does not apply to the attacker env");
+    return TD_OK;
+}
+
+extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    int rc = check_io(h, io);
+    if (rc != TD_OK) return rc;
+    TD_CUDA(h, cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    p.io = *io;
+    const int grid = grid_of(h), block = kWarpsPerCta * 32;
+    const size_t smem = smem_of(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->kind == TD_KIND_DEF) {
+        if (io->multi_action) td_step_kernel<TD_KIND_DEF, true><<<grid, block, smem, s>>>(p);
+        else td_step_kernel<TD_KIND_DEF, false><<<grid, block, smem, s>>>(p);
+    } else if (h->kind == TD_KIND_ATK) {
+        td_step_kernel<TD_KIND_ATK, false><<<grid, block, smem, s>>>(p);
+    } else {
+        if (io->multi_action) td_step_kernel<TD_KIND_2P, true><<<grid, block, smem, s>>>(p);
+        else td_step_kernel<TD_KIND_2P, false><<<grid, block, smem, s>>>(p);
+    }
+    TD_CUDA(h, cudaGetLastError());
+    h->steps += h->n_envs;
+    return TD_OK;
+}
+
+extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (!obs_dev) return fail(h, TD_E_INVALID, "td_observe: obs_dev is NULL");
+    if (h->n_maps < 1) return fail(h, TD_E_STATE, "td_observe: upload maps and reset first");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    td_observe_kernel<<<grid_of(h), kWarpsPerCta * 32, smem_of(h), (cudaStream_t)stream>>>(p, obs_dev);
+    TD_CUDA(h, cudaGetLastError());
+    return TD_OK;
+}
+
+extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (!host) return fail(h, TD_E_INVALID, "td_step_host: host is NULL");
+    int rc = check_io(h, io);
+    if (rc != TD_OK) return rc;
+    TD_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)h->n_envs, cells = (size_t)h->cells;
+    const size_t def_elems = io->multi_action ? n * 6 * cells : n;
+    if (h->kind != TD_KIND_ATK) {
+        if (!host->def_action_host) return fail(h, TD_E_INVALID, "td_step_host: def_action_host is required");
+        TD_CUDA(h, cudaMemcpyAsync((void *)io->def_action_dev, host->def_action_host, def_elems * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (h->kind != TD_KIND_DEF) {
+        if (!host->atk_action_host) return fail(h, TD_E_INVALID, "td_step_host: atk_action_host is required");
+        TD_CUDA(h, cudaMemcpyAsync((void *)io->atk_action_dev, host->atk_action_host, n * TD_ROADS * TD_CLUSTER * 8, cudaMemcpyHostToDevice, s));
+    }
+    if (io->opponent_dev && host->opponent_host)
+        TD_CUDA(h, cudaMemcpyAsync((void *)io->opponent_dev, host->opponent_host, n, cudaMemcpyHostToDevice, s));
+    rc = td_step(h, io, stream);
+    if (rc != TD_OK) return rc;
+#define TD_D2H(dst, src, bytes) \
+    if ((dst) && (src)) TD_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
+    TD_D2H(host->obs_host, io->obs_dev, n * TD_NCHANNELS * cells * sizeof(float));
+    TD_D2H(host->reward_host, io->reward_dev, n * sizeof(double));
+    TD_D2H(host->done_host, io->done_dev, n);
+    TD_D2H(host->win_host, io->win_dev, n);
+    TD_D2H(host->allow_next_host, io->allow_next_dev, n);
+    TD_D2H(host->real_def_host, io->real_def_dev, def_elems * 8);
+    TD_D2H(host->real_atk_host, io->real_atk_dev, n * TD_ROADS * TD_CLUSTER * 8);
+    TD_D2H(host->fail_def_host, io->fail_def_dev, n * sizeof(int32_t));
+    TD_D2H(host->fail_atk_host, io->fail_atk_dev, n * 4 * sizeof(int32_t));
+#undef TD_D2H
+    TD_CUDA(h, cudaStreamSynchronize(s));
+    return TD_OK;
+}
+
+extern "C" int td_get_state(td_handle *h, int first_env, int n, void *blob)
+{
+    if (!h) return TD_E_INVALID;
+    if (!blob || first_env < 0 || n < 1 || first_env + n > h->n_envs) return fail(h, TD_E_INVALID, "td_get_state: bad range");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaDeviceSynchronize());
+    TD_CUDA(h, cudaMemcpy(blob, h->records + (size_t)first_env * h->record_bytes, (size_t)n * h->record_bytes, cudaMemcpyDeviceToHost));
+    return TD_OK;
+}
+
+extern "C" int td_set_state(td_handle *h, int first_env, int n, const void *blob)
+{
+    if (!h) return TD_E_INVALID;
+    if (!blob || first_env < 0 || n < 1 || first_env + n > h->n_envs) return fail(h, TD_E_INVALID, "td_set_state: bad range");
+    const uint8_t *b = static_cast<const uint8_t *>(blob);
+    for (int i = 0; i < n; ++i) {
+        const td_env_header *hd = reinterpret_cast<const td_env_header *>(b + (size_t)i * h->record_bytes);
+        if (hd->n_towers > TD_CAP_TOWERS || hd->n_enemies > TD_CAP_ENEMIES || hd->map_id < 0 ||
+            (h->n_maps > 0 && hd->map_id >= h->n_maps) || hd->rng_pos < 0 || hd->rng_pos > kMtWords)
+            return fail(h, TD_E_INVALID, "td_set_state: record header out of range");
+        const td_tower_rec *tw = reinterpret_cast<const td_tower_rec *>(b + (size_t)i * h->record_bytes + kOffTowers);
+        for (int t = 0; t < hd->n_towers; ++t)
+            if (tw[t].loc >= h->cells || (tw[t].type_lv >> 2) >= TD_NLV) return fail(h, TD_E_INVALID, "td_set_state: bad tower record");
+        const td_enemy_rec *en = reinterpret_cast<const td_enemy_rec *>(b + (size_t)i * h->record_bytes + kOffEnemies);
+        for (int e = 0; e < hd->n_enemies; ++e)
+            if (en[e].loc >= h->cells || (en[e].type_lv >> 2) >= TD_NLV) return fail(h, TD_E_INVALID, "td_set_state: bad enemy record");
+    }
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaDeviceSynchronize());
+    TD_CUDA(h, cudaMemcpy(h->records + (size_t)first_env * h->record_bytes, blob, (size_t)n * h->record_bytes, cudaMemcpyHostToDevice));
+    return TD_OK;
+}
+
+extern "C" int td_get_stats(td_handle *h, td_stats *out, void *stream)
+{
+    if (!h || !out) return TD_E_INVALID;
+    TD_CUDA(h, cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    td_stats_kernel<<<1, 256, 0, s>>>(h->stats, h->n_envs, h->steps, h->stats_dev);
+    TD_CUDA(h, cudaGetLastError());
+    TD_CUDA(h, cudaMemcpyAsync(out, h->stats_dev, sizeof(td_stats), cudaMemcpyDeviceToHost, s));
+    TD_CUDA(h, cudaStreamSynchronize(s));
+    return TD_OK;
+}
+
+extern "C" int td_reset_stats(td_handle *h, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaMemsetAsync(h->stats, 0, (size_t)h->n_envs * sizeof(EnvStats), (cudaStream_t)stream));
+    h->steps = 0;
+    return TD_OK;
+}

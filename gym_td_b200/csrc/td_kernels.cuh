@@ -1,0 +1,1111 @@
+// td_kernels.cuh -- sm_100a kernels for the batched gym-TD board step.
+//
+// One warp advances one game instance.  The env record (header, tower list, enemy list, map6)
+// is staged from HBM into the warp's private shared-memory slice with 16-byte coalesced loads,
+// all game rules run warp-cooperatively on that slice (lanes = towers or enemies, ballots and
+// shuffles instead of loops where the reference loops), the (45, L, L) float32 observation is
+// written with streaming 128-bit stores, and the live prefix of the record is written back.
+// No block-level synchronisation exists anywhere: warps never communicate.
+//
+// Reference semantics followed (file:line under gym_TD/envs/):
+//   (a) defender decode + build/LvUp/destruct  TDDefense.py:38-77, TDMulti.py:65-115, TDBoard.py:226-293,
+//                                               TDElements.py:134-170 (incl. the lvup argument swap)
+//   (b) cluster summon                          TDBoard.py:199-224, TDAttack.py:36-46, TDMulti.py:88-98
+//   (c) advance / leak / end condition          TDBoard.py:319-346, 370-385
+//   (d) sort, target selection, damage          TDBoard.py:305-317, TDElements.py:19-28, 67-132
+//   (e) reward + economy                        TDBoard.py:298-299, 315, 337-338, 348-353
+//   (f) enemy statistics + observation          TDBoard.py:355-365, 85-144
+//   scripted opponents                          TDGymBasic.py:81-196 (CPython `random` semantics)
+//
+// Compile with -fmad=false: the reference never fuses a multiply-add, and costs, LP, margins and
+// rewards are compared bit for bit.
+#pragma once
+#include "../../include/td_b200.h"
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace td {
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kHdrBytes = 64;
+constexpr int kTowerBytes = 16;
+constexpr int kEnemyBytes = 24;
+constexpr int kOffTowers = kHdrBytes;
+constexpr int kOffEnemies = kOffTowers + TD_CAP_TOWERS * kTowerBytes;     // 576
+constexpr int kOffMap6 = kOffEnemies + TD_CAP_ENEMIES * kEnemyBytes;      // 2112
+constexpr int kMapHdrBytes = 16;
+constexpr int kMtWords = 624;
+
+// Derived constant tables (uploaded by td_set_config).
+struct DevConfig {
+    double enemy_LP[TD_NTYPES][TD_NLV];
+    double enemy_speed[TD_NTYPES][TD_NLV];
+    double enemy_defense[TD_NTYPES][TD_NLV];
+    double enemy_cost[TD_NTYPES][TD_NLV];
+    double tower_attack[TD_NTYPES][TD_NLV];
+    double tower_cost[TD_NTYPES][TD_NLV];
+    double tower_intv[TD_NTYPES][TD_NLV];     // effective interval by (type, lv): lv1 = tower_cost[t][1] (sic)
+    double tower_refund[TD_NTYPES][TD_NLV];   // Tower.cost by (type, lv): lv1 = cost[t][0] + interval[t][1] (sic)
+    int tower_range[TD_NTYPES][TD_NLV];
+    int tower_splash[TD_NTYPES][TD_NLV];
+    double destruct_return, frozen_ratio, atk_init_cost, def_init_cost, max_cost;
+    double reward_kill, penalty_leak, reward_time, rate_init, rate_final, def_rate, upgrade_at;
+    int frozen_time, base_LP, tower_distance, atk_interval, def_interval, max_steps;
+};
+
+__constant__ DevConfig cc;
+
+struct MapHdr {            // 16 bytes, head of a map-pool record
+    uint16_t start[3];
+    uint16_t end;
+    uint8_t num_roads;
+    uint8_t maxd_p1;       // max(map[4]) + 1
+    uint8_t pad[6];
+};
+
+struct EnvStats {          // 32 bytes per env, written only when an episode ends
+    double return_sum;
+    uint32_t episodes, wins, length_sum, kills, leaks, flags;
+};
+
+struct StepParams {
+    uint8_t *records;          // [n][record_bytes]
+    const uint8_t *maps;       // [n_maps][map_bytes]
+    uint32_t *mt;              // [n][624] scripted-opponent generator words (may be NULL)
+    EnvStats *stats;           // [n]
+    int n_envs, n_maps, map_stride;
+    int L, cells, cells_pad, record_bytes, map_bytes, smem_per_warp, scratch_off;
+    int difficulty;
+    int opponent_seeded;
+    td_step_io io;
+};
+
+// ------------------------------------------------------------------------------------------------
+// per-warp context: pointers into the warp's shared-memory slice + uniform registers
+
+struct Ctx {
+    td_env_header *hdr;
+    td_tower_rec *tw;
+    td_enemy_rec *en;
+    uint8_t *map6;
+    MapHdr *mh;
+    uint8_t *cells;
+    uint8_t *dist;
+    uint8_t *scratch;          // >= 512 bytes (+128 byte index scratch behind it)
+    int lane, L, ncells, cells_pad;
+    // uniform copies of hot header fields (identical in all lanes)
+    double cost_def, cost_atk;
+    int nt, ne, base_LP, steps, def_cd, atk_cd, fail, flags;
+    // opponent generator cursor
+    uint32_t *mt;
+    uint32_t win;
+    int mt_pos, win_k, win_n;
+};
+
+__device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16, int lane)
+{
+    int4 *d = reinterpret_cast<int4 *>(dst);
+    const int4 *s = reinterpret_cast<const int4 *>(src);
+    for (int q = lane; q < n16; q += 32) d[q] = s[q];
+}
+
+__device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, const StepParams &p)
+{
+    w.hdr = reinterpret_cast<td_env_header *>(slice);
+    w.tw = reinterpret_cast<td_tower_rec *>(slice + kOffTowers);
+    w.en = reinterpret_cast<td_enemy_rec *>(slice + kOffEnemies);
+    w.map6 = slice + kOffMap6;
+    uint8_t *m = slice + p.record_bytes;
+    w.mh = reinterpret_cast<MapHdr *>(m);
+    w.cells = m + kMapHdrBytes;
+    w.dist = w.cells + p.cells_pad;
+    w.scratch = slice + p.scratch_off;
+    w.lane = threadIdx.x & 31;
+    w.L = p.L;
+    w.ncells = p.cells;
+    w.cells_pad = p.cells_pad;
+    w.mt = nullptr;
+    w.win = 0; w.mt_pos = 0; w.win_k = 0; w.win_n = 0;
+}
+
+__device__ __forceinline__ void load_static_map(Ctx &w, const StepParams &p, int map_id)
+{
+    warp_copy16(w.mh, p.maps + (size_t)map_id * p.map_bytes, p.map_bytes >> 4, w.lane);
+}
+
+__device__ __forceinline__ void pull_header(Ctx &w)
+{
+    const td_env_header *h = w.hdr;
+    w.cost_def = h->cost_def;
+    w.cost_atk = h->cost_atk;
+    w.nt = h->n_towers;
+    w.ne = h->n_enemies;
+    w.base_LP = h->base_LP;
+    w.steps = h->steps;
+    w.def_cd = h->defender_cd;
+    w.atk_cd = h->attacker_cd;
+    w.flags = h->flags;
+    w.fail = TD_FC_SUCCESS;
+    w.mt_pos = h->rng_pos;
+}
+
+__device__ __forceinline__ void push_header(Ctx &w)
+{
+    if (w.lane == 0) {
+        td_env_header *h = w.hdr;
+        h->cost_def = w.cost_def;
+        h->cost_atk = w.cost_atk;
+        h->n_towers = (uint8_t)w.nt;
+        h->n_enemies = (uint8_t)w.ne;
+        h->base_LP = w.base_LP;
+        h->steps = w.steps;
+        h->defender_cd = (int16_t)w.def_cd;
+        h->attacker_cd = (int16_t)w.atk_cd;
+        h->flags = (uint8_t)w.flags;
+        h->rng_pos = w.mt_pos;
+    }
+}
+
+// Stage one env: header + map6 first (independent), then the live prefixes and the static map.
+__device__ __forceinline__ void load_env(Ctx &w, const StepParams &p, const uint8_t *rec)
+{
+    if (w.lane < 4) reinterpret_cast<int4 *>(w.hdr)[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
+    warp_copy16(w.map6, rec + kOffMap6, p.cells_pad >> 4, w.lane);
+    __syncwarp();
+    pull_header(w);
+    warp_copy16(w.tw, rec + kOffTowers, w.nt, w.lane);                       // 16 B per tower
+    warp_copy16(w.en, rec + kOffEnemies, (w.ne * 3 + 1) >> 1, w.lane);        // 24 B per enemy
+    load_static_map(w, p, w.hdr->map_id);
+    __syncwarp();
+}
+
+__device__ __forceinline__ void store_env(Ctx &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
+{
+    push_header(w);
+    __syncwarp();
+    if (w.lane < 4) reinterpret_cast<int4 *>(rec)[w.lane] = reinterpret_cast<const int4 *>(w.hdr)[w.lane];
+    warp_copy16(rec + kOffTowers, w.tw, w.nt, w.lane);
+    warp_copy16(rec + kOffEnemies, w.en, (w.ne * 3 + 1) >> 1, w.lane);
+    if (map6_dirty) warp_copy16(rec + kOffMap6, w.map6, p.cells_pad >> 4, w.lane);
+}
+
+// TDGymBasic.reset (:37-55) + TDBoard.__init__ (:63-79): fresh episode on map `map_id`.
+__device__ __forceinline__ void reset_env(Ctx &w, const StepParams &p, int map_id, bool reload_map)
+{
+    if (reload_map) {
+        __syncwarp();
+        load_static_map(w, p, map_id);
+        __syncwarp();
+    }
+    for (int q = w.lane; q < (p.cells_pad >> 2); q += 32) {
+        uint32_t c4 = reinterpret_cast<const uint32_t *>(w.cells)[q];
+        reinterpret_cast<uint32_t *>(w.map6)[q] = c4 & 0x01010101u;           // map[6] = 1 on road cells
+    }
+    w.cost_def = cc.def_init_cost;
+    w.cost_atk = cc.atk_init_cost;
+    w.nt = 0;
+    w.ne = 0;
+    w.base_LP = cc.base_LP;
+    w.steps = 0;
+    w.def_cd = 0;
+    w.atk_cd = 0;
+    w.fail = TD_FC_SUCCESS;
+    if (w.lane == 0) {
+        w.hdr->map_id = map_id;
+        w.hdr->ep_return = 0.0;
+        w.hdr->ep_kills = 0;
+        w.hdr->ep_leaks = 0;
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// CPython-compatible MT19937 consumer (random.Random): one tempered window of <= 32 words per fill
+
+__device__ __forceinline__ void mt_twist(uint32_t *mt, int lane)
+{
+    // mt[k] = mt[k+397] ^ f(mt[k], mt[k+1]); three dependency-free phases + the last word
+    auto f = [](uint32_t a, uint32_t b) {
+        uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+        return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    };
+    uint32_t v[8];
+    // phase A: k in [0, 227) reads old mt[k], mt[k+1], mt[k+397]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < 227) v[i] = mt[k + 397] ^ f(mt[k], mt[k + 1]); }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < 227) mt[k] = v[i]; }
+    __syncwarp();
+    // phase B: k in [227, 454) reads new mt[k-227], old mt[k], mt[k+1]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = 227 + lane + 32 * i; if (k < 454) v[i] = mt[k - 227] ^ f(mt[k], mt[k + 1]); }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = 227 + lane + 32 * i; if (k < 454) mt[k] = v[i]; }
+    __syncwarp();
+    // phase C: k in [454, 623)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = 454 + lane + 32 * i; if (k < 623) v[i] = mt[k - 227] ^ f(mt[k], mt[k + 1]); }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { int k = 454 + lane + 32 * i; if (k < 623) mt[k] = v[i]; }
+    __syncwarp();
+    if (lane == 0) mt[623] = mt[396] ^ f(mt[623], mt[0]);
+    __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t mt_next(Ctx &w)
+{
+    if (w.win_k == w.win_n) {
+        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane); w.mt_pos = 0; }
+        int n = kMtWords - w.mt_pos;
+        w.win_n = n < 32 ? n : 32;
+        uint32_t y = w.lane < w.win_n ? w.mt[w.mt_pos + w.lane] : 0u;
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        w.win = y;
+        w.win_k = 0;
+    }
+    uint32_t r = __shfl_sync(kFull, w.win, w.win_k);
+    ++w.win_k;
+    ++w.mt_pos;
+    return r;
+}
+
+// random._randbelow_with_getrandbits(n), 1 <= n < 2^31
+__device__ __forceinline__ int py_randbelow(Ctx &w, int n)
+{
+    int shift = __clz(n);            // 32 - bit_length(n)
+    uint32_t r = mt_next(w) >> shift;
+    while (r >= (uint32_t)n) r = mt_next(w) >> shift;
+    return (int)r;
+}
+
+__device__ __forceinline__ double py_random(Ctx &w)
+{
+    uint32_t a = mt_next(w) >> 5, b = mt_next(w) >> 6;
+    return __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// (a) defender operations -- all arguments and results are warp-uniform
+
+__device__ __forceinline__ void diamond_add(Ctx &w, int loc, int delta)
+{
+    const int L = w.L, D = cc.tower_distance, W = 2 * D + 1;
+    const int r0 = loc / L, c0 = loc - r0 * L;
+    for (int k = w.lane; k < W * W; k += 32) {
+        int i = k / W - D, j = k % W - D;
+        int r = r0 + i, c = c0 + j;
+        if (abs(i) + abs(j) <= D && r >= 0 && r < L && c >= 0 && c < L)
+            w.map6[r * L + c] = (uint8_t)(w.map6[r * L + c] + delta);
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ bool tower_build(Ctx &w, int t, int loc, bool &map6_dirty)   // TDBoard.py:226-247
+{
+    const double cost = cc.tower_cost[t][0];
+    if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
+    if (w.map6[loc] > 0) { w.fail = TD_FC_INVALID_POSITION; return false; }
+    if (w.nt >= TD_CAP_TOWERS) { w.flags |= 2; w.fail = TD_FC_INVALID_POSITION; return false; }
+    if (w.lane == 0) {
+        td_tower_rec &r = w.tw[w.nt];
+        r.cd = 0.0;
+        r.loc = (uint16_t)loc;
+        r.type_lv = (uint8_t)t;
+    }
+    w.nt += 1;
+    w.cost_def = __dsub_rn(w.cost_def, cost);
+    diamond_add(w, loc, +1);
+    map6_dirty = true;
+    w.fail = TD_FC_SUCCESS;
+    return true;
+}
+
+__device__ __forceinline__ int find_tower(const Ctx &w, int loc)
+{
+    bool m = w.lane < w.nt && w.tw[w.lane].loc == loc;
+    unsigned b = __ballot_sync(kFull, m);
+    return b ? __ffs(b) - 1 : -1;
+}
+
+__device__ __forceinline__ bool tower_lvup(Ctx &w, int loc)                              // TDBoard.py:249-271
+{
+    int idx = find_tower(w, loc);
+    if (idx < 0) { w.fail = TD_FC_UNKNOWN_TARGET; return false; }
+    int tl = w.tw[idx].type_lv, ty = tl & 3, lv = tl >> 2;
+    if (lv >= TD_NLV - 1) { w.fail = TD_FC_LV_MAX; return false; }
+    const double cost = cc.tower_cost[ty][lv + 1];
+    if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
+    __syncwarp();
+    if (w.lane == 0) w.tw[idx].type_lv = (uint8_t)(ty | ((lv + 1) << 2));
+    __syncwarp();
+    w.cost_def = __dsub_rn(w.cost_def, cost);
+    w.fail = TD_FC_SUCCESS;
+    return true;
+}
+
+__device__ __forceinline__ bool tower_destruct(Ctx &w, int loc, bool &map6_dirty)        // TDBoard.py:273-293
+{
+    int idx = find_tower(w, loc);
+    if (idx < 0) { w.fail = TD_FC_UNKNOWN_TARGET; return false; }
+    int tl = w.tw[idx].type_lv;
+    double c = __dadd_rn(w.cost_def, __dmul_rn(cc.tower_refund[tl & 3][tl >> 2], cc.destruct_return));
+    w.cost_def = cc.max_cost < c ? cc.max_cost : c;
+    // remove from the list, keeping the order of the rest
+    td_tower_rec mine;
+    bool mv = w.lane > idx && w.lane < w.nt;
+    if (mv) mine = w.tw[w.lane];
+    __syncwarp();
+    if (mv) w.tw[w.lane - 1] = mine;
+    __syncwarp();
+    w.nt -= 1;
+    diamond_add(w, loc, -1);
+    map6_dirty = true;
+    w.fail = TD_FC_SUCCESS;
+    return true;
+}
+
+// Discrete action (TDDefense.py:61-77, TDMulti.py:100-115).  Returns success.
+__device__ __forceinline__ bool decode_discrete(Ctx &w, long long a, long long &real, int &failcode, bool &dirty)
+{
+    const long long nop = 6ll * w.ncells;
+    real = nop;
+    failcode = 0;
+    if (w.def_cd != 0 || a == nop || (unsigned long long)a > (unsigned long long)nop) return false;
+    int ai = (int)a;
+    int act = ai / w.ncells, loc = ai - act * w.ncells;
+    bool res;
+    if (act < TD_NTYPES) res = tower_build(w, act, loc, dirty);
+    else if (act == TD_NTYPES) res = tower_lvup(w, loc);
+    else res = tower_destruct(w, loc, dirty);
+    if (res) { w.def_cd = cc.def_interval; real = a; }
+    failcode = w.fail;
+    return res;
+}
+
+// Multi-action Box(6, L, L) (TDDefense.py:40-60, TDMulti.py:65-84): r-major, c, then build 0..3, LvUp,
+// destruct inside a cell, every operation seeing the state left by the previous one.  32 cells are
+// screened per pass; a cell is skipped when none of its flagged operations can succeed in the
+// current state (no tower on it, and no flagged build that is both affordable and placeable).  The
+// screen is recomputed after every success because cost and map6 then change.
+__device__ __forceinline__ void decode_multi(Ctx &w, const long long *act, long long *real, bool &dirty)
+{
+    const int cells = w.ncells;
+    uint8_t *tower_at = w.scratch;      // cells bytes: 1 where a tower stands (scratch >= cells_pad here)
+    const bool enabled = w.def_cd == 0;
+    for (int q = w.lane; q < (w.cells_pad >> 2); q += 32) reinterpret_cast<uint32_t *>(tower_at)[q] = 0u;
+    __syncwarp();
+    if (w.lane < w.nt) tower_at[w.tw[w.lane].loc] = 1;
+    __syncwarp();
+    for (int base = 0; base < cells; base += 32) {
+        const int cell = base + w.lane;
+        unsigned flags = 0;          // bit ch set when action[ch][cell] == 1
+        if (cell < cells) {
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) {
+                long long v = __ldcs(act + (size_t)ch * cells + cell);
+                flags |= (v == 1 ? 1u : 0u) << ch;
+            }
+        }
+        unsigned done_mask = 0;      // successes of this lane's cell
+        if (enabled) {
+            unsigned pending = __ballot_sync(kFull, flags != 0);
+            while (pending) {
+                // screen with the current state
+                bool can = false;
+                if (flags) {
+                    if (tower_at[cell]) can = (flags & 0x30u) != 0 || false;
+                    if (!can && (flags & 0x0fu) && w.map6[cell] == 0) {
+#pragma unroll
+                        for (int t = 0; t < TD_NTYPES; ++t)
+                            can = can || (((flags >> t) & 1u) && !(w.cost_def < cc.tower_cost[t][0]));
+                    }
+                    // a flagged build on a free cell can create the tower that a flagged LvUp/destruct then hits
+                }
+                unsigned cand = __ballot_sync(kFull, can) & pending;
+                if (!cand) break;
+                int src = __ffs(cand) - 1;
+                unsigned f = __shfl_sync(kFull, flags, src);
+                int loc = base + src;
+                unsigned ok = 0;
+                for (int t = 0; t < TD_NTYPES; ++t)
+                    if ((f >> t) & 1u) if (tower_build(w, t, loc, dirty)) { ok |= 1u << t; if (w.lane == 0) tower_at[loc] = 1; __syncwarp(); }
+                if ((f >> 4) & 1u) if (tower_lvup(w, loc)) ok |= 1u << 4;
+                if ((f >> 5) & 1u) if (tower_destruct(w, loc, dirty)) { ok |= 1u << 5; if (w.lane == 0) tower_at[loc] = 0; __syncwarp(); }
+                if (ok) w.def_cd = cc.def_interval;
+                if (w.lane == src) done_mask = ok;
+                // cells up to and including src are finished
+                pending &= ~((2u << src) - 1u);
+            }
+        }
+        if (cell < cells && real) {
+#pragma unroll
+            for (int ch = 0; ch < 6; ++ch) __stcs(real + (size_t)ch * cells + cell, (long long)((done_mask >> ch) & 1u));
+        }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// (b) summon
+
+__device__ __forceinline__ void append_enemy(Ctx &w, int t, int lv, int start)
+{
+    if (w.ne >= TD_CAP_ENEMIES) { w.flags |= 1; return; }
+    if (w.lane == 0) {
+        td_enemy_rec &e = w.en[w.ne];
+        e.LP = cc.enemy_LP[t][lv];
+        e.margin = 0.0;
+        e.loc = (uint16_t)start;
+        e.type_lv = (uint8_t)(t | (lv << 2));
+        e.slowdown = 0;
+    }
+    w.ne += 1;
+}
+
+// TDBoard.py:199-224 for one road.  `mine` is this lane's slot value (lanes road*8..road*8+7 hold the
+// cluster); updated in place to the RealAction value.  Returns the bool of the (bool, list) tuple.
+__device__ __forceinline__ bool summon_cluster(Ctx &w, int road, long long &mine, int lane_base)
+{
+    const int start = w.mh->start[road];
+    const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
+    bool tried = false, summoned = false;
+#pragma unroll
+    for (int k = 0; k < TD_CLUSTER; ++k) {
+        long long t = __shfl_sync(kFull, mine, lane_base + k);
+        if (t < 0 || t >= TD_NTYPES) continue;               // 4 == enemy_types: empty slot
+        tried = true;
+        const double cost = cc.enemy_cost[(int)t][lv];
+        if (w.cost_atk < cost) {
+            if (w.lane == lane_base + k) mine = TD_NTYPES;
+        } else {
+            w.cost_atk = __dsub_rn(w.cost_atk, cost);
+            append_enemy(w, (int)t, lv, start);
+            summoned = true;
+        }
+    }
+    if (!summoned && tried) { w.fail = TD_FC_COST_SHORTAGE; return false; }
+    w.fail = TD_FC_SUCCESS;
+    return true;
+}
+
+// scripted attacker of the defender env: 8 x type t on one road (TDGymBasic.py:95-108)
+__device__ __forceinline__ void summon_uniform(Ctx &w, int t, int road)
+{
+    long long mine = t;
+    summon_cluster(w, road, mine, 0);   // every lane holds t, so any lane_base works
+}
+
+// ------------------------------------------------------------------------------------------------
+// scripted opponents on the device generator (TDGymBasic.py:81-196, random_agent=True)
+
+__device__ __forceinline__ void opponent_enemy(Ctx &w, int difficulty)
+{
+    if (w.atk_cd != 0) return;
+    if (difficulty == 0) {                                   // random_enemy_lv0
+        long long mine = 0;
+        for (int k = 0; k < TD_CLUSTER; ++k) { int t = py_randbelow(w, TD_NTYPES + 1); if (w.lane == k) mine = t; }
+        int road = py_randbelow(w, w.mh->num_roads);
+        summon_cluster(w, road, mine, 0);
+    } else {                                                 // random_enemy_lv1
+        int t = py_randbelow(w, TD_NTYPES);
+        int road = py_randbelow(w, w.mh->num_roads);
+        summon_uniform(w, t, road);
+    }
+    w.atk_cd = cc.atk_interval;                              // the returned tuple is always truthy
+}
+
+__device__ __forceinline__ void opponent_tower(Ctx &w, int difficulty, bool &dirty)
+{
+    if (w.def_cd != 0) return;
+    const int L = w.L;
+    if (difficulty == 0) {                                   // random_tower_lv0
+        int r = py_randbelow(w, L), c = py_randbelow(w, L), t = py_randbelow(w, TD_NTYPES);
+        if (tower_build(w, t, r * L + c, dirty)) w.def_cd = cc.def_interval;
+        return;
+    }
+    int act = py_randbelow(w, 3);                            // random_tower_lv1
+    if (act == 0) {
+        // road cells in row-major order
+        uint16_t *list = reinterpret_cast<uint16_t *>(w.scratch);
+        int n = 0;
+        for (int base = 0; base < w.ncells; base += 32) {
+            int c = base + w.lane;
+            bool on = c < w.ncells && (w.cells[c] & 1);
+            unsigned b = __ballot_sync(kFull, on);
+            if (on) list[n + __popc(b & ((1u << w.lane) - 1u))] = (uint16_t)c;
+            n += __popc(b);
+        }
+        __syncwarp();
+        for (int i = n - 1; i >= 1; --i) {                   // random.shuffle
+            int j = py_randbelow(w, i + 1);
+            if (w.lane == 0) { uint16_t t = list[i]; list[i] = list[j]; list[j] = t; }
+        }
+        __syncwarp();
+        int t = py_randbelow(w, TD_NTYPES);
+        for (int k = 0; k < n; ++k) {
+            int di = py_randbelow(w, 25);
+            int cell = list[k];
+            int r = cell / L + (di / 5 - 2), c = cell % L + (di % 5 - 2);
+            if (r < 0 || r >= L || c < 0 || c >= L) continue;
+            if (tower_build(w, t, r * L + c, dirty)) { w.def_cd = cc.def_interval; return; }
+            if (w.fail == TD_FC_COST_SHORTAGE) return;
+        }
+    } else {
+        if (w.nt == 0) return;
+        if (act == 2 && py_random(w) > .01) return;
+        int id = py_randbelow(w, w.nt);
+        int loc = w.tw[id].loc;
+        bool ok = act == 1 ? tower_lvup(w, loc) : tower_destruct(w, loc, dirty);
+        if (ok) w.def_cd = cc.def_interval;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (c)(d)(e) TDBoard.step, returns the defender reward; kills/leaks for the statistics
+
+struct EnemyRegs {
+    double LP, margin;
+    int loc, tl, slow, r, c;
+    bool valid;
+};
+
+__device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_out)
+{
+    const int L = w.L, lane = w.lane;
+    double reward = __dadd_rn(0.0, cc.reward_time);
+    w.steps += 1;
+    const double progress = (double)w.steps / (double)cc.max_steps;
+
+    const int ne = w.ne, nt = w.nt;
+    const int nchunk = (ne + 31) >> 5;                       // 0, 1 or 2
+    EnemyRegs E[2];
+    double *keys = reinterpret_cast<double *>(w.scratch);    // [64]
+    uint8_t *erow = w.scratch + 512, *ecol = w.scratch + 576;  // [64] each
+
+    // ---- load enemies into registers, sort key = dist - margin (TDBoard.py:305)
+    bool unsorted = false;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int e = lane + 32 * k;
+        E[k].valid = e < ne;
+        if (E[k].valid) {
+            const td_enemy_rec &x = w.en[e];
+            E[k].LP = x.LP; E[k].margin = x.margin; E[k].loc = x.loc; E[k].tl = x.type_lv; E[k].slow = x.slowdown;
+            keys[e] = __dsub_rn((double)w.dist[E[k].loc], E[k].margin);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int e = lane + 32 * k;
+        bool inv = E[k].valid && e > 0 && keys[e - 1] > keys[e];
+        unsorted = unsorted || inv;
+    }
+    unsorted = __any_sync(kFull, unsorted);
+    if (unsorted) {
+        // stable rank = #(key smaller) + #(equal key, earlier position)
+        int rank[2] = {0, 0};
+        for (int j = 0; j < ne; ++j) {
+            double kj = keys[j];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                int e = lane + 32 * k;
+                if (E[k].valid) { double ke = keys[e]; rank[k] += (kj < ke || (kj == ke && j < e)) ? 1 : 0; }
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (E[k].valid) {
+                td_enemy_rec &x = w.en[rank[k]];
+                x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
+                x.slowdown = (uint8_t)E[k].slow;
+            }
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            int e = lane + 32 * k;
+            if (E[k].valid) {
+                const td_enemy_rec &x = w.en[e];
+                E[k].LP = x.LP; E[k].margin = x.margin; E[k].loc = x.loc; E[k].tl = x.type_lv; E[k].slow = x.slowdown;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        int e = lane + 32 * k;
+        if (E[k].valid) {
+            E[k].r = E[k].loc / L; E[k].c = E[k].loc - E[k].r * L;
+            erow[e] = (uint8_t)E[k].r; ecol[e] = (uint8_t)E[k].c;
+        }
+    }
+    __syncwarp();
+
+    // ---- towers choose targets: first enemy in list order within Chebyshev range, corpses included
+    //      (TDBoard.py:306-312, TDElements.py:72-132).  Positions do not change inside the tower loop, so
+    //      every tower's choice is independent: lane = tower.
+    uint8_t *fire = w.scratch + 640, *vict = w.scratch + 672;     // [32] each
+    if (lane < nt) {
+        td_tower_rec &T = w.tw[lane];
+        const int ty = T.type_lv & 3, lv = T.type_lv >> 2;
+        double cd = __dsub_rn(T.cd, 1.0);
+        int target = -1, victim = -1;
+        if (!(cd > 0.0)) {
+            const int rge = cc.tower_range[ty][lv];
+            const int tr = T.loc / L, tc = T.loc - tr * L;
+            for (int j = 0; j < ne; ++j) {
+                int dr = abs((int)erow[j] - tr), dc = abs((int)ecol[j] - tc);
+                if (max(dr, dc) <= rge) { target = j; break; }
+            }
+            if (target >= 0) {
+                cd = __dadd_rn(cd, cc.tower_intv[ty][lv]);
+                victim = target;
+                if (ty == 3) {                                // Frozen: first enemy within splash of the target
+                    const int sp = cc.tower_splash[ty][lv];
+                    if (sp > 0) {
+                        const int r0 = erow[target], c0 = ecol[target];
+                        for (int j = 0; j < ne; ++j) {
+                            int dr = abs((int)erow[j] - r0), dc = abs((int)ecol[j] - c0);
+                            if (max(dr, dc) <= sp) { victim = j; break; }
+                        }
+                    }
+                }
+            }
+            if (cd < 0.0) cd = 0.0;
+        }
+        T.cd = cd;
+        fire[lane] = (uint8_t)(target < 0 ? 0xff : target);
+        vict[lane] = (uint8_t)(victim < 0 ? 0xff : victim);
+    }
+    __syncwarp();
+
+    // ---- damage in tower order: lane = enemy (TDElements.py:19-28)
+    bool hit[2] = {false, false};
+    if (ne > 0) {
+        double defense[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) defense[k] = E[k].valid ? cc.enemy_defense[E[k].tl & 3][E[k].tl >> 2] : 0.0;
+        for (int t = 0; t < nt; ++t) {
+            const int f = fire[t];
+            if (f == 0xff) continue;
+            const int tl = w.tw[t].type_lv, ty = tl & 3, lv = tl >> 2;
+            const double atk = cc.tower_attack[ty][lv];
+            const double floor_ = __dmul_rn(atk, .05);
+            const bool magic = (ty == 1 || ty == 3);
+            const int sp = cc.tower_splash[ty][lv];
+            const int fr = erow[f], fc = ecol[f], v = vict[t];
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                if (k >= nchunk) break;
+                int e = lane + 32 * k;
+                bool h;
+                if (ty == 2) h = E[k].valid && max(abs(E[k].r - fr), abs(E[k].c - fc)) <= sp;
+                else if (ty == 3) h = E[k].valid && e == v;
+                else h = E[k].valid && e == f;
+                if (h) {
+                    double dmg;
+                    if (magic) dmg = atk;
+                    else { dmg = __dsub_rn(atk, defense[k]); if (!(dmg > 0.0)) dmg = 0.0; }
+                    if (dmg < floor_) dmg = floor_;
+                    E[k].LP = __dsub_rn(E[k].LP, dmg);
+                    if (E[k].LP <= 0.0) E[k].LP = 0.0;
+                    if (ty == 3) E[k].slow = cc.frozen_time;
+                    hit[k] = true;
+                }
+            }
+        }
+    }
+
+    // ---- remove the killed, move the rest, remove the leaked (TDBoard.py:313-346)
+    int kills = 0, leaks = 0, kept_before = 0;
+    const int end = w.mh->end;
+    int newidx[2];
+    bool keep[2];
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        bool killed = E[k].valid && hit[k] && !(E[k].LP > 0.0);
+        bool leaked = false;
+        if (E[k].valid && !killed) {
+            const double speed = cc.enemy_speed[E[k].tl & 3][E[k].tl >> 2];
+            if (E[k].slow > 0) { E[k].margin = __dadd_rn(E[k].margin, __dmul_rn(speed, cc.frozen_ratio)); E[k].slow -= 1; }
+            else E[k].margin = __dadd_rn(E[k].margin, speed);
+            while (E[k].margin >= 1.0) {
+                E[k].margin = __dsub_rn(E[k].margin, 1.0);
+                int d = (w.cells[E[k].loc] >> 4) & 3;
+                E[k].loc += (d == 0) ? 1 : (d == 1) ? -1 : (d == 2) ? L : -L;
+                if (E[k].loc == end) { leaked = true; break; }
+            }
+        }
+        keep[k] = E[k].valid && !killed && !leaked;
+        unsigned bk = __ballot_sync(kFull, killed), bl = __ballot_sync(kFull, leaked), bs = __ballot_sync(kFull, keep[k]);
+        kills += __popc(bk);
+        leaks += __popc(bl);
+        newidx[k] = kept_before + __popc(bs & ((1u << lane) - 1u));
+        kept_before += __popc(bs);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+        if (keep[k]) {
+            td_enemy_rec &x = w.en[newidx[k]];
+            x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
+            x.slowdown = (uint8_t)E[k].slow;
+        }
+    w.ne = kept_before;
+    __syncwarp();
+
+    reward = __dadd_rn(reward, __dmul_rn(cc.reward_kill, (double)kills));
+    const bool has_base = cc.base_LP >= 0;
+    for (int i = 0; i < leaks; ++i) {
+        if (has_base && w.base_LP > 0) reward = __dsub_rn(reward, cc.penalty_leak);
+        if (has_base) w.base_LP = max(w.base_LP - 1, 0);
+    }
+
+    // ---- economy (TDBoard.py:348-353)
+    double rate;
+    if (progress >= 0.5) rate = cc.rate_final;
+    else rate = __dadd_rn(__dmul_rn(cc.rate_init, __dsub_rn(1.0, progress)), __dmul_rn(cc.rate_final, progress));
+    double ca = __dadd_rn(w.cost_atk, rate);
+    w.cost_atk = cc.max_cost < ca ? cc.max_cost : ca;
+    double cd = __dadd_rn(w.cost_def, cc.def_rate);
+    w.cost_def = cc.max_cost < cd ? cc.max_cost : cd;
+
+    kills_out = kills;
+    leaks_out = leaks;
+    return reward;
+}
+
+// ------------------------------------------------------------------------------------------------
+// (f) observation: dense planes with streaming float4 stores, then the sparse one-hots / enemy
+//     statistics as 4-byte stores on top (ordered after the dense pass by __syncwarp).
+
+__device__ __forceinline__ void fill_planes(float *o, int first_plane, int n_planes, int cells, float v, int lane)
+{
+    float4 *p = reinterpret_cast<float4 *>(o + (size_t)first_plane * cells);
+    const int n4 = (n_planes * cells) >> 2;
+    const float4 x = make_float4(v, v, v, v);
+    for (int q = lane; q < n4; q += 32) __stcs(p + q, x);
+}
+
+__device__ __forceinline__ void fill_planes_scalar(float *o, int first_plane, int n_planes, int cells, float v, int lane)
+{
+    float *p = o + (size_t)first_plane * cells;
+    for (int q = lane; q < n_planes * cells; q += 32) __stcs(p + q, v);
+}
+
+__device__ __forceinline__ void write_obs(Ctx &w, float *o)
+{
+    const int lane = w.lane, cells = w.ncells;
+    const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+    const bool has_base = cc.base_LP >= 0;
+    const float v5 = has_base ? (float)((double)w.base_LP / (double)cc.base_LP) : 1.f;
+    const float v11 = (float)(w.cost_def / cc.max_cost);
+    const float v12 = (float)(w.cost_atk / cc.max_cost);
+    const float v13 = (float)((double)w.steps / (double)cc.max_steps);
+    const float maxd = (float)w.mh->maxd_p1;
+    float vb[TD_NTYPES], vs[TD_NTYPES];
+#pragma unroll
+    for (int t = 0; t < TD_NTYPES; ++t) {
+        vb[t] = w.cost_def >= cc.tower_cost[t][0] ? 1.f : 0.f;
+        vs[t] = (float)(w.cost_def / cc.enemy_cost[t][0] / 8.0);
+    }
+    if (vec) {
+        const int c4 = cells >> 2;
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells);
+        const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist);
+        const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6);
+        for (int q = lane; q < c4; q += 32) {
+            uchar4 c = cb[q];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                __stcs(o4 + k * c4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
+                                                    (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
+        }
+        fill_planes(o, 4, 1, cells, 0.f, lane);
+        fill_planes(o, 5, 1, cells, v5, lane);
+        fill_planes(o, 6, 3, cells, 0.f, lane);
+        for (int q = lane; q < c4; q += 32) {
+            uchar4 d = db[q];
+            __stcs(o4 + 9 * c4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
+                                                __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
+        }
+        fill_planes(o, 10, 1, cells, 0.f, lane);
+        fill_planes(o, 11, 1, cells, v11, lane);
+        fill_planes(o, 12, 1, cells, v12, lane);
+        fill_planes(o, 13, 1, cells, v13, lane);
+        for (int q = lane; q < c4; q += 32) {
+            uchar4 m = mb[q];
+            __stcs(o4 + 14 * c4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
+                                                 m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
+        }
+        fill_planes(o, 15, 6, cells, 0.f, lane);
+#pragma unroll
+        for (int t = 0; t < TD_NTYPES; ++t) fill_planes(o, 21 + t, 1, cells, vb[t], lane);
+        fill_planes(o, 25, 16, cells, 0.f, lane);
+#pragma unroll
+        for (int t = 0; t < TD_NTYPES; ++t) fill_planes(o, 41 + t, 1, cells, vs[t], lane);
+    } else {
+        for (int q = lane; q < cells; q += 32) {
+            uint8_t c = w.cells[q];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) __stcs(o + (size_t)k * cells + q, (float)((c >> k) & 1));
+            __stcs(o + (size_t)9 * cells + q, __fdiv_rn((float)w.dist[q], maxd));
+            __stcs(o + (size_t)14 * cells + q, w.map6[q] == 0 ? 1.f : 0.f);
+        }
+        fill_planes_scalar(o, 4, 1, cells, 0.f, lane);
+        fill_planes_scalar(o, 5, 1, cells, v5, lane);
+        fill_planes_scalar(o, 6, 3, cells, 0.f, lane);
+        fill_planes_scalar(o, 10, 1, cells, 0.f, lane);
+        fill_planes_scalar(o, 11, 1, cells, v11, lane);
+        fill_planes_scalar(o, 12, 1, cells, v12, lane);
+        fill_planes_scalar(o, 13, 1, cells, v13, lane);
+        fill_planes_scalar(o, 15, 6, cells, 0.f, lane);
+        for (int t = 0; t < TD_NTYPES; ++t) fill_planes_scalar(o, 21 + t, 1, cells, vb[t], lane);
+        fill_planes_scalar(o, 25, 16, cells, 0.f, lane);
+        for (int t = 0; t < TD_NTYPES; ++t) fill_planes_scalar(o, 41 + t, 1, cells, vs[t], lane);
+    }
+
+    // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
+    float *ratio = reinterpret_cast<float *>(w.scratch);       // [64]
+    const int ne = w.ne;
+    for (int e = lane; e < ne; e += 32) {
+        const td_enemy_rec &x = w.en[e];
+        ratio[e] = (float)(x.LP / cc.enemy_LP[x.type_lv & 3][x.type_lv >> 2]);
+    }
+    __syncwarp();   // also orders the dense stores above before the sparse stores below
+    if (lane == 0) o[(size_t)4 * cells + w.mh->end] = 1.f;
+    if (lane < w.mh->num_roads) o[(size_t)(6 + lane) * cells + w.mh->start[lane]] = 1.f;
+    if (lane < w.nt) {
+        const td_tower_rec &T = w.tw[lane];
+        o[(size_t)(15 + (T.type_lv >> 2)) * cells + T.loc] = 1.f;
+        o[(size_t)(17 + (T.type_lv & 3)) * cells + T.loc] = 1.f;
+    }
+    for (int e = lane; e < ne; e += 32) {
+        const int loc = w.en[e].loc, ty = w.en[e].type_lv & 3;
+        float mn = 1.f, mx = 0.f, sum = 0.f, cnt = 0.f;
+        bool leader = true;
+        for (int j = 0; j < ne; ++j) {
+            if (w.en[j].loc == loc && (w.en[j].type_lv & 3) == ty) {
+                if (j < e) leader = false;
+                float r = ratio[j];
+                mn = r < mn ? r : mn;
+                mx = r > mx ? r : mx;
+                sum = __fadd_rn(sum, r);
+                cnt += 1.f;
+            }
+        }
+        if (leader) {
+            o[(size_t)(25 + ty) * cells + loc] = mn;
+            o[(size_t)(29 + ty) * cells + loc] = mx;
+            o[(size_t)(33 + ty) * cells + loc] = __fdiv_rn(sum, cnt);
+            o[(size_t)(37 + ty) * cells + loc] = cnt * 0.125f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+
+extern __shared__ __align__(16) uint8_t td_smem[];
+
+template <int KIND, bool MULTI>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) td_step_kernel(const StepParams p)
+{
+    const int warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * kWarpsPerCta + warp;
+    if (env >= p.n_envs) return;
+    Ctx w;
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
+    uint8_t *rec = p.records + (size_t)env * p.record_bytes;
+    load_env(w, p, rec);
+    const int lane = w.lane;
+    const td_step_io &io = p.io;
+    bool dirty = false;
+    const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
+                                 !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
+    if (device_opponent) w.mt = p.mt + (size_t)env * kMtWords;
+
+    // cooldowns (TDDefense.py:38-39)
+    w.atk_cd = max(w.atk_cd - 1, 0);
+    w.def_cd = max(w.def_cd - 1, 0);
+
+    long long real_def = 6ll * w.ncells;
+    int fail_def = 0;
+    bool def_ok = false;
+    int fail_atk[TD_ROADS] = {0, 0, 0}, n_fail_atk = 0;
+    long long atk_mine = TD_NTYPES;
+
+    auto defender = [&]() {
+        if (MULTI) {
+            decode_multi(w, reinterpret_cast<const long long *>(io.def_action_dev) + (size_t)env * 6 * w.ncells,
+                         io.real_def_dev ? reinterpret_cast<long long *>(io.real_def_dev) + (size_t)env * 6 * w.ncells : nullptr,
+                         dirty);
+        } else {
+            long long a = io.def_action_dev[env];
+            def_ok = decode_discrete(w, a, real_def, fail_def, dirty);
+        }
+    };
+    auto attacker = [&]() {
+        if (lane < TD_ROADS * TD_CLUSTER) atk_mine = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane];
+        if (w.atk_cd == 0) {
+            const int nr = w.mh->num_roads;
+            for (int i = 0; i < nr; ++i) {
+                if (!(KIND == TD_KIND_2P && MULTI)) {
+                    bool skip = __all_sync(kFull, (lane < i * 8 || lane >= i * 8 + 8) || atk_mine == TD_NTYPES);
+                    if (skip) { fail_atk[n_fail_atk++] = 0; continue; }     // TDAttack.py:39-41
+                }
+                long long before = atk_mine;
+                bool res = summon_cluster(w, i, atk_mine, i * 8);
+                if (KIND == TD_KIND_2P) { atk_mine = before; w.atk_cd = cc.atk_interval; }   // tuple truthiness
+                else if (res) w.atk_cd = cc.atk_interval;
+                fail_atk[n_fail_atk++] = w.fail;
+            }
+            if (KIND == TD_KIND_2P && MULTI) n_fail_atk = 0;
+        }
+    };
+
+    if (KIND == TD_KIND_DEF) {
+        defender();
+        if (io.opponent_dev != nullptr) {
+            int o = io.opponent_dev[env];
+            if (o != 0xff && w.atk_cd == 0) {
+                summon_uniform(w, o & 3, min((o >> 4) & 3, w.mh->num_roads - 1));
+                w.atk_cd = cc.atk_interval;
+            }
+        } else if (device_opponent) opponent_enemy(w, p.difficulty);
+    } else if (KIND == TD_KIND_ATK) {
+        attacker();
+        if (device_opponent) opponent_tower(w, p.difficulty, dirty);
+    } else {
+        attacker();
+        defender();
+    }
+    __syncwarp();
+
+    int kills, leaks;
+    double reward = board_step(w, kills, leaks);
+    if (KIND == TD_KIND_ATK) reward = -reward;
+
+    const bool has_base = cc.base_LP >= 0;
+    const bool done = (has_base && w.base_LP <= 0) || w.steps >= cc.max_steps;
+    const bool def_wins = !has_base || w.base_LP > 0;
+    const bool atk_wins = !has_base || w.base_LP <= 0;
+    const bool my_win = KIND == TD_KIND_ATK ? atk_wins : def_wins;
+
+    if (lane == 0) {
+        if (io.reward_dev) io.reward_dev[env] = reward;
+        if (io.done_dev) io.done_dev[env] = done ? 1 : 0;
+        if (io.win_dev) io.win_dev[env] = done ? (my_win ? 1 : 0) : -1;
+        if (io.allow_next_dev) io.allow_next_dev[env] = (uint8_t)((w.def_cd <= 1 ? 1 : 0) | (w.atk_cd <= 1 ? 2 : 0));
+        if (!MULTI && KIND != TD_KIND_ATK) {
+            if (io.real_def_dev) io.real_def_dev[env] = real_def;
+            if (io.fail_def_dev) io.fail_def_dev[env] = fail_def;
+        } else if (io.fail_def_dev) io.fail_def_dev[env] = 0;
+        if (KIND != TD_KIND_DEF && io.fail_atk_dev) {
+            int4 f = make_int4(n_fail_atk, fail_atk[0], fail_atk[1], fail_atk[2]);
+            reinterpret_cast<int4 *>(io.fail_atk_dev)[env] = f;
+        }
+        td_env_header *h = w.hdr;
+        h->ep_return = __dadd_rn(h->ep_return, reward);
+        h->ep_kills = (uint16_t)(h->ep_kills + kills);
+        h->ep_leaks = (uint16_t)(h->ep_leaks + leaks);
+        if (done) {
+            EnvStats &s = p.stats[env];
+            s.return_sum = __dadd_rn(s.return_sum, h->ep_return);
+            s.episodes += 1;
+            s.wins += my_win ? 1 : 0;
+            s.length_sum += (uint32_t)w.steps;
+            s.kills += h->ep_kills;
+            s.leaks += h->ep_leaks;
+        }
+        if (w.flags) p.stats[env].flags |= (uint32_t)w.flags;
+    }
+    if (KIND != TD_KIND_DEF && io.real_atk_dev && lane < TD_ROADS * TD_CLUSTER)
+        io.real_atk_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane] = atk_mine;
+    (void)def_ok;
+    __syncwarp();
+
+    if (done && io.auto_reset) {
+        int next = (w.hdr->map_id + p.map_stride) % p.n_maps;
+        if (lane == 0) w.hdr->episode += 1;
+        reset_env(w, p, next, true);
+        dirty = true;
+    }
+    if (io.obs_dev) write_obs(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells);
+    __syncwarp();
+    store_env(w, p, rec, dirty);
+}
+
+// reset (mask / explicit map ids) and observation-only kernels
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids, float *obs)
+{
+    const int warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * kWarpsPerCta + warp;
+    if (env >= p.n_envs) return;
+    if (mask && !mask[env]) return;
+    Ctx w;
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
+    uint8_t *rec = p.records + (size_t)env * p.record_bytes;
+    if (w.lane < 4) reinterpret_cast<int4 *>(w.hdr)[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
+    __syncwarp();
+    pull_header(w);
+    int id = map_ids ? map_ids[env] : env % p.n_maps;
+    id = ((id % p.n_maps) + p.n_maps) % p.n_maps;
+    reset_env(w, p, id, true);
+    if (obs) write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+    __syncwarp();
+    store_env(w, p, rec, true);
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const StepParams p, float *obs)
+{
+    const int warp = threadIdx.x >> 5;
+    const int env = blockIdx.x * kWarpsPerCta + warp;
+    if (env >= p.n_envs) return;
+    Ctx w;
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
+    load_env(w, p, p.records + (size_t)env * p.record_bytes);
+    write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+}
+
+// deterministic reduction of the per-env statistics: one block, fixed order
+__global__ void __launch_bounds__(256) td_stats_kernel(const EnvStats *s, int n, long long steps, td_stats *out)
+{
+    __shared__ double r[256];
+    __shared__ long long acc[256][6];
+    const int t = threadIdx.x;
+    double rs = 0.0;
+    long long a[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = t; i < n; i += 256) {
+        rs += s[i].return_sum;
+        a[0] += s[i].episodes; a[1] += s[i].length_sum; a[2] += s[i].wins;
+        a[3] += s[i].kills; a[4] += s[i].leaks; a[5] += s[i].flags ? 1 : 0;
+    }
+    r[t] = rs;
+    for (int k = 0; k < 6; ++k) acc[t][k] = a[k];
+    __syncthreads();
+    for (int stride = 128; stride > 0; stride >>= 1) {
+        if (t < stride) {
+            r[t] += r[t + stride];
+            for (int k = 0; k < 6; ++k) acc[t][k] += acc[t + stride][k];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        out->return_sum = r[0];
+        out->episodes = acc[0][0]; out->length_sum = acc[0][1]; out->wins = acc[0][2];
+        out->kills = acc[0][3]; out->leaks = acc[0][4]; out->overflow_envs = acc[0][5];
+        out->steps = steps;
+    }
+}
+
+} // namespace td

@@ -1,0 +1,257 @@
+/*
+ * td_b200.h -- C ABI of the B200-native batched gym-TD board step.
+ *
+ * This is the drop-in boundary: the entry points below are what a binding of the
+ * reference's operator interface for this path would call.  The reference has no
+ * FFI (it is pure Python); the interface being replaced is the `TDBoard` method
+ * set plus the three env wrappers' step() bodies:
+ *
+ *   td_create / td_destroy      <- TDBoard.__init__            gym_TD/envs/TDBoard.py:14-79
+ *                                  TDGymBasic.__init__          gym_TD/envs/TDGymBasic.py:18-28
+ *   td_set_config               <- paramConfig / config         gym_TD/envs/TDParam.py:1-100
+ *   td_mapgen*                  <- TDRoadGen.create_road_v2     gym_TD/envs/TDRoadGen.py:4-199
+ *                                  + map planes                 gym_TD/envs/TDBoard.py:31-59
+ *   td_upload_maps              <- (the np_random map stream of TDGymBasic.reset, :42-51)
+ *   td_reset                    <- TDGymBasic.reset             gym_TD/envs/TDGymBasic.py:37-55
+ *   td_step                     <- TDDefense.step               gym_TD/envs/TDDefense.py:34-87
+ *                                  TDAttack.step                gym_TD/envs/TDAttack.py:27-56
+ *                                  TDMulti.step                 gym_TD/envs/TDMulti.py:46-138
+ *                                  (which call tower_build/lvup/destruct, summon_cluster, step,
+ *                                   done, get_states: TDBoard.py:199-385, 85-144)
+ *   td_observe                  <- TDBoard.get_states           gym_TD/envs/TDBoard.py:85-144
+ *   td_get_state / td_set_state <- (direct attribute access on board/env objects)
+ *   td_seed_opponent            <- random.seed / `random` module use in TDGymBasic.py:81-196
+ *
+ * Conventions: every function returns 0 on success or a negative TD_E_* code; no C++
+ * exception crosses the boundary; td_last_error() gives the message for the last failure
+ * on a handle (or of td_create when h == NULL).  All kernels are launched asynchronously
+ * on the caller's stream (a cudaStream_t passed as void*).  Pointers named *_dev are device
+ * pointers owned by the caller (e.g. torch tensors); *_host are host pointers.  A handle
+ * belongs to one device and is not thread-safe: the caller serialises calls on it.
+ * There is no CPU fallback: without a CUDA device every compute entry point fails with
+ * TD_E_CUDA.
+ */
+#ifndef TD_B200_H
+#define TD_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TD_ABI_VERSION 1
+
+enum { TD_OK = 0, TD_E_INVALID = -1, TD_E_CUDA = -2, TD_E_ALLOC = -3, TD_E_STATE = -4,
+       TD_E_OVERFLOW = -5 };
+
+/* env kinds (TDDefense / TDAttack / TDMulti) */
+enum { TD_KIND_DEF = 0, TD_KIND_ATK = 1, TD_KIND_2P = 2 };
+
+/* gym_TD/utils/fail_code.py:1-6 */
+enum { TD_FC_SUCCESS = 0, TD_FC_COST_SHORTAGE = 1, TD_FC_INVALID_POSITION = 2, TD_FC_LV_MAX = 3,
+       TD_FC_UNKNOWN_TARGET = 4, TD_FC_IMPOSSIBLE_CLUSTER = 5 };
+
+#define TD_NTYPES 4     /* enemy_types == tower_types (TDParam.py:6-7) */
+#define TD_NLV 2        /* max_enemy_lv == max_tower_lv == 1 (TDParam.py:3-4) */
+#define TD_CLUSTER 8    /* max_cluster_length (TDParam.py:110) */
+#define TD_ROADS 3      /* max_num_of_roads (TDParam.py:111) */
+#define TD_NCHANNELS 45 /* TDBoard.n_channels(), TDBoard.py:146-154 */
+#define TD_CAP_TOWERS 32
+#define TD_CAP_ENEMIES 64
+#define TD_MAX_L 64
+
+/* snapshot of TDParam.config + hyper_parameters (same field meaning as the reference) */
+typedef struct td_config {
+    double enemy_LP[TD_NTYPES][TD_NLV];
+    double enemy_speed[TD_NTYPES][TD_NLV];
+    double enemy_defense[TD_NTYPES][TD_NLV];
+    double enemy_cost[TD_NTYPES][TD_NLV];
+    double tower_attack[TD_NTYPES][TD_NLV];
+    double tower_cost[TD_NTYPES][TD_NLV];
+    double tower_attack_interval[TD_NTYPES][TD_NLV];
+    int32_t tower_range[TD_NTYPES][TD_NLV];
+    int32_t tower_splash_range[TD_NTYPES][TD_NLV];
+    double tower_destruct_return;
+    double frozen_ratio;
+    double attacker_init_cost, defender_init_cost, max_cost;
+    double reward_kill, penalty_leak, reward_time;
+    double attacker_cost_init_rate, attacker_cost_final_rate, defender_cost_rate;
+    double enemy_upgrade_at;
+    int32_t frozen_time;
+    int32_t base_LP;            /* < 0 means None (no leakage ending) */
+    int32_t tower_distance;
+    int32_t attacker_action_interval, defender_action_interval;
+    int32_t max_episode_steps;
+    int32_t max_tower_lv;       /* must be 1 in this build */
+    int32_t pad_;
+} td_config;
+
+/* One generated map in transfer form (host).  cells[i]: bits 0-3 = map[0..3] (road, road1..3),
+ * bits 4-5 = map[5] (direction 0..3); dist[i] = map[4].  TDBoard.py:31-59. */
+typedef struct td_map {
+    int32_t map_size;
+    int32_t num_roads;
+    int32_t start[TD_ROADS];    /* r*L + c */
+    int32_t end;
+    int32_t max_dist;           /* np.max(map[4]) */
+    int32_t n_randint;          /* randint() calls the generator made (seed-skip budget accounting) */
+    uint8_t cells[TD_MAX_L * TD_MAX_L];
+    uint8_t dist[TD_MAX_L * TD_MAX_L];
+} td_map;
+
+typedef struct td_handle td_handle;
+
+/* Per-step device buffers.  Unused pointers may be NULL.  Leading dimension is n_envs. */
+typedef struct td_step_io {
+    /* inputs */
+    const int64_t *def_action_dev;   /* DEF/2P: [n] Discrete, or [n,6,L,L] when multi_action != 0 */
+    const int64_t *atk_action_dev;   /* ATK/2P: [n,3,8] */
+    const uint8_t *opponent_dev;     /* DEF only, optional host-resolved scripted attacker (random_enemy_lv1):
+                                        [n] bytes, type | road<<4, 0xFF = attacker does nothing.  When NULL the
+                                        on-device CPython-compatible generator seeded by td_seed_opponent is used;
+                                        if that was never seeded there is no scripted opponent. */
+    int32_t multi_action;            /* hyper_parameters.allow_multiple_actions */
+    int32_t auto_reset;              /* re-initialise finished envs from the map pool inside the step */
+    /* outputs */
+    float *obs_dev;                  /* [n,45,L,L] float32; may be NULL to skip the observation */
+    double *reward_dev;              /* [n] */
+    uint8_t *done_dev;               /* [n] */
+    int8_t *win_dev;                 /* [n] -1 None / 0 / 1; 2P: defender view (attacker = !defender when done) */
+    uint8_t *allow_next_dev;         /* [n] bit0 defender, bit1 attacker (AllowNextMove) */
+    int64_t *real_def_dev;           /* [n] Discrete RealAction, or [n,6,L,L] in multi_action mode */
+    int64_t *real_atk_dev;           /* [n,3,8] */
+    int32_t *fail_def_dev;           /* [n] */
+    int32_t *fail_atk_dev;           /* [n,4]: count, then up to 3 codes (FailCode list of TDAttack/TDMulti) */
+} td_step_io;
+
+/* byte offsets inside one env record, for td_get_state / td_set_state blobs */
+typedef struct td_layout {
+    int32_t record_bytes;
+    int32_t off_header, off_towers, off_enemies, off_map6;
+    int32_t tower_stride, enemy_stride;
+    int32_t cap_towers, cap_enemies;
+    int32_t map_record_bytes;
+    int32_t mt_words;           /* 624 */
+    int32_t pad_;
+} td_layout;
+
+/* header of an env record (what td_get_state returns at off_header) */
+typedef struct td_env_header {
+    double cost_def;
+    double cost_atk;
+    double ep_return;
+    int32_t base_LP;
+    int32_t steps;
+    int32_t map_id;
+    int32_t episode;
+    int16_t defender_cd;
+    int16_t attacker_cd;
+    uint8_t n_towers;
+    uint8_t n_enemies;
+    uint8_t flags;              /* bit0 enemy overflow, bit1 tower overflow (sticky) */
+    uint8_t pad0;
+    uint16_t ep_kills;
+    uint16_t ep_leaks;
+    int32_t rng_pos;            /* position in the opponent MT19937 state (0..624) */
+    int32_t pad1;
+    int32_t pad2;
+} td_env_header;                /* 64 bytes */
+
+typedef struct td_tower_rec {   /* 16 bytes, list order */
+    double cd;
+    uint16_t loc;
+    uint8_t type_lv;            /* type | lv << 2 */
+    uint8_t scratch[5];
+} td_tower_rec;
+
+typedef struct td_enemy_rec {   /* 24 bytes, list order */
+    double LP;
+    double margin;
+    uint16_t loc;
+    uint8_t type_lv;            /* type | lv << 2 */
+    uint8_t slowdown;
+    uint8_t scratch[4];
+} td_enemy_rec;
+
+/* episode statistics, summed over the handle's envs (deterministic reduction on device) */
+typedef struct td_stats {
+    double return_sum;
+    int64_t episodes;
+    int64_t length_sum;
+    int64_t wins;               /* from the env's own perspective (2P: defender) */
+    int64_t kills;
+    int64_t leaks;
+    int64_t overflow_envs;      /* envs whose tower/enemy capacity overflowed (results invalid) */
+    int64_t steps;              /* env-steps executed since creation */
+} td_stats;
+
+int td_abi_version(void);
+const char *td_last_error(const td_handle *h);
+void td_default_config(td_config *cfg);
+
+/* host-only: reference-order road generator on a NumPy-legacy MT19937 stream.
+ * num_roads <= 0: draw it first from the same stream like TDGymBasic.reset (:42).
+ * Returns 1 if the seed is valid, 0 if the reference generator would raise or exceed
+ * `budget` randint calls (seed-skip rule), <0 on error. */
+int td_mapgen(uint32_t seed, int map_size, int num_roads, int budget, td_map *out);
+/* n seeds in parallel on `threads` host threads; valid_out[i] as above. first-valid search:
+ * if skip_invalid != 0, seed i is advanced (s <- s+1) until valid and seeds_inout[i] is updated. */
+int td_mapgen_batch(uint32_t *seeds_inout, int n, int map_size, int num_roads, int budget,
+                    int skip_invalid, int threads, td_map *out, int32_t *valid_out);
+
+int td_create(const td_config *cfg, int env_kind, int map_size, int n_envs, int device, td_handle **out);
+int td_destroy(td_handle *h);
+int td_set_config(td_handle *h, const td_config *cfg);
+int td_get_layout(const td_handle *h, td_layout *out);
+
+/* replace the device map pool by n_maps host maps */
+int td_upload_maps(td_handle *h, const td_map *maps_host, int n_maps);
+/* auto-reset schedule: a finished env takes map (map_id + stride) % n_maps */
+int td_set_map_stride(td_handle *h, int stride);
+
+/* (re)start envs: mask_dev NULL = all; map_ids_dev NULL = env i takes map i % n_maps.
+ * obs_dev may be NULL. */
+int td_reset(td_handle *h, const uint8_t *mask_dev, const int32_t *map_ids_dev, float *obs_dev, void *stream);
+
+/* seed the per-env scripted-opponent generators: states_host is [n_envs][625] uint32
+ * (624 MT19937 words + position, i.e. random.Random(s).getstate()[1]). */
+int td_seed_opponent(td_handle *h, const uint32_t *states_host, int first_env, int n);
+/* scripted opponent level (difficulty kwarg of TDDefense/TDAttack); default 1 */
+int td_set_difficulty(td_handle *h, int difficulty);
+
+int td_step(td_handle *h, const td_step_io *io, void *stream);
+/* observation of the current state only (kernel (f) alone) */
+int td_observe(td_handle *h, float *obs_dev, void *stream);
+
+/* Host-buffer variant (the gym-facing call): copies the actions host->device, steps, copies
+ * the small outputs (and the observation if obs_host != NULL) device->host, and synchronises.
+ * The *_dev members of io are used as the device staging buffers; host pointers should be pinned. */
+typedef struct td_host_io {
+    const int64_t *def_action_host;
+    const int64_t *atk_action_host;
+    const uint8_t *opponent_host;
+    float *obs_host;
+    double *reward_host;
+    uint8_t *done_host;
+    int8_t *win_host;
+    uint8_t *allow_next_host;
+    int64_t *real_def_host;
+    int64_t *real_atk_host;
+    int32_t *fail_def_host;
+    int32_t *fail_atk_host;
+} td_host_io;
+int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, void *stream);
+
+/* raw env records (td_layout) to/from host; blob is n * record_bytes */
+int td_get_state(td_handle *h, int first_env, int n, void *blob_host);
+int td_set_state(td_handle *h, int first_env, int n, const void *blob_host);
+/* opponent generator states, [n][625] */
+int td_get_opponent(td_handle *h, int first_env, int n, uint32_t *states_host);
+
+int td_get_stats(td_handle *h, td_stats *out, void *stream);
+int td_reset_stats(td_handle *h, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,56 @@
+"""GPU parity: CUDA engine (through the C ABI) vs the CPU oracle, bit for bit, every step."""
+import pytest
+
+from tests import parity_util as PU
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("L", [10, 20, 30])
+def test_def_discrete_device_opponent(L):
+    n = PU.run_parity("def", L, n_envs=48, steps=1200, seed=L, opponent="device", difficulty=1)
+    assert n > 10000
+
+
+@pytest.mark.parametrize("L", [10, 20])
+def test_def_discrete_opponent_lv0(L):
+    assert PU.run_parity("def", L, n_envs=24, steps=600, seed=L + 1, opponent="device", difficulty=0) > 3000
+
+
+def test_def_discrete_host_stream():
+    assert PU.run_parity("def", 10, n_envs=32, steps=600, seed=3, opponent="stream") > 3000
+
+
+@pytest.mark.parametrize("L", [10, 20, 30])
+def test_atk_device_opponent(L):
+    assert PU.run_parity("atk", L, n_envs=32, steps=1200, seed=L + 2, opponent="device", difficulty=1) > 3000
+
+
+def test_atk_opponent_lv0():
+    assert PU.run_parity("atk", 10, n_envs=24, steps=600, seed=5, opponent="device", difficulty=0) > 2000
+
+
+@pytest.mark.parametrize("L", [10, 20, 30])
+def test_multi_discrete(L):
+    assert PU.run_parity("2p", L, n_envs=32, steps=1200, seed=L + 3, opponent="none") > 3000
+
+
+@pytest.mark.parametrize("L", [10, 20])
+def test_def_multi_action(L):
+    assert PU.run_parity("def", L, n_envs=24, steps=600, seed=L + 4, multi=True, opponent="device") > 2000
+
+
+def test_multi_multi_action():
+    assert PU.run_parity("2p", 20, n_envs=16, steps=600, seed=9, multi=True, opponent="none") > 2000
+
+
+def test_config_overrides():
+    ov = dict(base_LP=None, defender_action_interval=3, attacker_action_interval=2)
+    assert PU.run_parity("def", 10, n_envs=16, steps=1200, seed=21, cfg_overrides=ov) > 2000
+    assert PU.run_parity("atk", 10, n_envs=16, steps=1200, seed=22, cfg_overrides=ov) > 2000
+    ov = dict(defender_init_cost=60, attacker_init_cost=50, defender_cost_rate=.7)
+    assert PU.run_parity("2p", 20, n_envs=16, steps=600, seed=23, cfg_overrides=ov, opponent="none") > 2000
+
+
+def test_odd_map_size_scalar_store_path():
+    assert PU.run_parity("def", 15, n_envs=16, steps=400, seed=31) > 1000
