@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched gym-TD board step on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload def-small] [--impl reference]
+
+One "step" = one lockstep pass of the fused step kernel over the whole batch of game instances
+of one GPU (action decode, scripted opponent, board dynamics, reward/done and the full
+(45, L, L) float32 observation write), with finished instances restarted in place.
+Under torchrun (N > 1) every rank steps its own batch (weak scaling, no data-path collective);
+NCCL carries only the episode-statistics all-reduce.  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (env id, kind, L, envs per GPU, multi_action, algorithmic bytes per env-step = SURVEY.md 8(d))
+    "def-small": ("TD-def-small-v0", "def", 10, 65536, False, 4 * 45 * 100 + 8 + 24),
+    "def-middle-multi": ("TD-def-middle-v0", "def", 20, 32768, True, 4 * 45 * 400 + 19200 + 19216),
+    "atk-small": ("TD-atk-small-v0", "atk", 10, 65536, False, 4 * 45 * 100 + 192 + 208),
+    "2p-large": ("TD-2p-large-v0", "2p", 30, 16384, False, 4 * 45 * 900 + 200 + 216),
+    "def-middle": ("TD-def-middle-v0", "def", 20, 32768, False, 4 * 45 * 400 + 8 + 24),
+    "def-large": ("TD-def-large-v0", "def", 30, 16384, False, 4 * 45 * 900 + 8 + 24),
+}
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="def-small", choices=sorted(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--preroll", type=int, default=1300, help="untimed steps to de-synchronise episodes")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    return ap.parse_args()
+
+
+def config_of(args, n_envs):
+    env_id, kind, L, _, multi, bpe = WORKLOADS[args.workload]
+    return {
+        "workload": "%s batched, %d envs/GPU, %s actions, scripted opponent lv1, auto-reset from a map pool"
+                    % (env_id, n_envs, "Box(6,L,L) multi" if multi else
+                       ("Discrete" if kind == "def" else "cluster (3,8)" if kind == "atk" else "Dict")),
+        "env_id": env_id, "map_size": L, "envs_per_gpu": n_envs,
+        "global_envs": n_envs * args.gpus, "parallelism": "env-shard x%d" % args.gpus,
+        "l2": "per-step output (%.0f MB) and env records exceed the 126 MB L2; no flush needed"
+              % (n_envs * 45 * L * L * 4 / 1e6),
+        "algorithmic_bytes_per_env_step": bpe,
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+
+class Clocks(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thread = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+            except ValueError:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline
+
+def cpu_reference_sample(kind, L, steps_per_worker, pool=None):
+    from oracle import cpu_baseline as CB
+    own = pool is None
+    pool = pool or CB.ReferencePool()
+    n, wall = pool.run(kind, L, steps_per_worker)
+    cores = pool.workers
+    if own:
+        pool.close()
+    return n, wall, cores
+
+
+def run_reference_arm(args):
+    """The reference's own CPU implementation of the path, all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    env_id, kind, L, n_envs, multi, _ = WORKLOADS[args.workload]
+    n_envs = args.envs or n_envs
+    from oracle import cpu_baseline as CB
+    cfg = config_of(args, n_envs)
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 state / f32 observation", "data": "synthetic", "config": cfg}
+    cores = os.cpu_count() or 1
+    if CB.reference_available() and not multi:
+        kind_name = "reference"
+        per_worker = 400                       # env-steps per worker per bench step (~60 ms of Python)
+        pool = CB.ReferencePool(cores)
+        for _ in range(max(args.warmup, 1)):
+            pool.run(kind, L, per_worker)
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(args.steps):
+            n, _w = pool.run(kind, L, per_worker)
+            total += n
+        wall = time.perf_counter() - t0
+        pool.close()
+        sample = ("unmodified Python reference (gym_TD via gym stub), %d processes x %d env-steps per step, "
+                  "%d steps, independent env instances, random actions" % (cores, per_worker, args.steps))
+    else:
+        kind_name = "port"
+        per_thread = 20000
+        for _ in range(max(min(args.warmup, 3), 1)):
+            CB.run_port(L, per_thread, cores)
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(args.steps):
+            n, _w = CB.run_port(L, per_thread, cores)
+            total += n
+        wall = time.perf_counter() - t0
+        sample = "C restatement (oracle/td_oracle.c), %d threads x %d env-steps per step" % (cores, per_thread)
+    value = total / wall
+    line.update(value=value, ms_per_step=1e3 * wall / args.steps,
+                cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": kind_name, "sample": sample},
+                e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from gym_td_b200.vec_env import TDVecEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world if world > 1 else 1
+
+    env_id, kind, L, n_envs, multi, bytes_per_env_step = WORKLOADS[args.workload]
+    n_envs = args.envs or n_envs
+    env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
+                   env_offset=1_000_000 * rank, multi_action=multi)
+    env.reset()
+
+    # pre-generated synthetic actions, resident in HBM (excluded from the timed region)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    A = 16
+    def_pool = atk_pool = None
+    if kind != "atk":
+        if multi:
+            def_pool = torch.randint(0, 3, (4, n_envs, 6, L, L), dtype=torch.int64, device=dev, generator=g)
+        else:
+            def_pool = torch.randint(0, 6 * L * L + 1, (A, n_envs), dtype=torch.int64, device=dev, generator=g)
+    if kind != "def":
+        atk_pool = torch.randint(0, 5, (A, n_envs, 3, 8), dtype=torch.int64, device=dev, generator=g)
+
+    def action(k):
+        d = def_pool[k % def_pool.shape[0]] if def_pool is not None else None
+        a = atk_pool[k % atk_pool.shape[0]] if atk_pool is not None else None
+        return d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.preroll):
+        env.step(action(k))
+    for k in range(args.warmup):
+        env.step(action(k))
+    env.engine.reset_stats()
+    barrier()
+
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.25)
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for k in range(args.steps):
+        env.step(action(k))
+    end.record()
+    barrier()
+    ms = start.elapsed_time(end)
+    clk = clocks.stop() if rank == 0 else None
+    stats = env.allreduce_stats()          # NCCL: the only collective of the path
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = n_envs * n_gpus * args.steps / (ms * 1e-3)
+
+    # end to end through the host-buffer API: pinned host actions in, reward/done/info out, every step
+    e2e = None
+    if not args.no_e2e:
+        hd = ha = None
+        if kind != "atk":
+            hd = [def_pool[i].cpu().pin_memory() for i in range(min(4, def_pool.shape[0]))]
+        if kind != "def":
+            ha = [atk_pool[i].cpu().pin_memory() for i in range(4)]
+
+        def haction(k):
+            d = hd[k % len(hd)] if hd is not None else None
+            a = ha[k % len(ha)] if ha is not None else None
+            return d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+
+        ke = max(10, args.steps // 3)
+        for k in range(3):
+            env.step_host(haction(k))
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(ke):
+            out = env.step_host(haction(k))
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        h2d, d2h = env.host_bytes_per_step(False)
+        e2e = {"value": n_envs * n_gpus * ke / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": ke,
+               "note": "td_step_host: pinned host actions -> device, fused step, reward/done/win/allow/"
+                       "RealAction/FailCode -> host, stream sync every step; the observation stays in HBM "
+                       "for the on-device learner (see e2e_host_obs for the variant that also copies it)"}
+        e2e_obs = None
+        if rank == 0 and world == 1:
+            ko = 5
+            env.step_host(haction(0), want_obs=True)
+            t0 = time.perf_counter()
+            for k in range(ko):
+                env.step_host(haction(k), want_obs=True)
+            wall = time.perf_counter() - t0
+            h2d, d2h = env.host_bytes_per_step(True)
+            e2e_obs = {"value": n_envs * ko / wall, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "steps": ko,
+                       "note": "as e2e plus the full float32 observation copied to pinned host memory (PCIe-bound)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks, peak_src = {}, "fallback"
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    kernel_ms = ms / args.steps                      # one fused kernel per step, timed on its own stream
+    achieved = bytes_per_env_step * n_envs / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tr.get(args.workload, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 state / f32 observation", "data": "synthetic",
+        "config": dict(config_of(args, n_envs), preroll_steps=args.preroll),
+        "gpu_launches": args.steps,
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": "td_step_kernel<%s>" % kind, "algorithmic_bytes_per_launch": bytes_per_env_step * n_envs},
+        "episode_stats": stats,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+        if e2e_obs is not None:
+            line["e2e_host_obs"] = e2e_obs
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as CB
+        cores = os.cpu_count() or 1
+        if CB.reference_available() and not multi:
+            per_worker = 6000                          # ~1 s of Python per worker
+            pool = CB.ReferencePool(cores)
+            pool.run(kind, L, 300)
+            n, wall = 0, 0.0
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 12.0:
+                a, b = pool.run(kind, L, per_worker)
+                n += a
+                wall += b
+            pool.close()
+            line["cpu_baseline"] = {"value": n / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+                                    "sample": "unmodified Python reference %s via gym stub: %d processes, %d env-steps "
+                                              "in %.1f s, independent instances, random actions" % (env_id, cores, n, wall)}
+        n, wall = CB.run_port(L, 400000, cores)
+        port = {"value": n / wall, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "C restatement oracle/td_oracle.c, TD-def L=%d, %d threads x 400000 env-steps" % (L, cores)}
+        if "cpu_baseline" in line:
+            line["cpu_port"] = port
+        else:
+            line["cpu_baseline"] = port
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -401,6 +401,34 @@ extern "C" int td_seed_opponent(td_handle *h, const uint32_t *states, int first_
     return TD_OK;
 }
 
+// CPython random.seed(int) for 0 <= seed < 2^32: init_by_array([seed]) (Modules/_randommodule.c)
+static void python_seed_state(uint32_t seed, uint32_t *st625)
+{
+    uint32_t *mt = st625;
+    mt[0] = 19650218u;
+    for (int i = 1; i < kMtWords; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+    int i = 1;
+    for (int k = kMtWords; k; --k) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1664525u)) + seed;   // key = [seed], j stays 0
+        if (++i >= kMtWords) { mt[0] = mt[kMtWords - 1]; i = 1; }
+    }
+    for (int k = kMtWords - 1; k; --k) {
+        mt[i] = (mt[i] ^ ((mt[i - 1] ^ (mt[i - 1] >> 30)) * 1566083941u)) - (uint32_t)i;
+        if (++i >= kMtWords) { mt[0] = mt[kMtWords - 1]; i = 1; }
+    }
+    mt[0] = 0x80000000u;
+    st625[kMtWords] = (uint32_t)kMtWords;
+}
+
+extern "C" int td_seed_opponent_python(td_handle *h, const uint32_t *seeds, int first_env, int n)
+{
+    if (!h) return TD_E_INVALID;
+    if (!seeds || n < 1) return fail(h, TD_E_INVALID, "td_seed_opponent_python: bad range");
+    std::vector<uint32_t> states((size_t)n * (kMtWords + 1));
+    for (int i = 0; i < n; ++i) python_seed_state(seeds[i], &states[(size_t)i * (kMtWords + 1)]);
+    return td_seed_opponent(h, states.data(), first_env, n);
+}
+
 extern "C" int td_get_opponent(td_handle *h, int first_env, int n, uint32_t *states)
 {
     if (!h) return TD_E_INVALID;

@@ -24,6 +24,17 @@ struct InvalidSeed {};
 // MT19937 as seeded by numpy.random.RandomState(int): init_genrand(seed)
 class LegacyStream {
 public:
+    LegacyStream(const uint32_t *state625, int budget) : calls_(0), budget_(budget)
+    {
+        memcpy(mt_, state625, sizeof(mt_));
+        pos_ = (int)state625[624];
+        if (pos_ < 0 || pos_ > 624) pos_ = 624;
+    }
+    void save(uint32_t *state625) const
+    {
+        memcpy(state625, mt_, sizeof(mt_));
+        state625[624] = (uint32_t)pos_;
+    }
     LegacyStream(uint32_t seed, int budget) : pos_(624), calls_(0), budget_(budget)
     {
         mt_[0] = seed;
@@ -247,10 +258,8 @@ void fill_map(const std::vector<Road> &roads, int L, td_map *m)
     m->max_dist = maxd;
 }
 
-int generate_one(uint32_t seed, int L, int num_roads, int budget, td_map *out)
+int generate_from(LegacyStream &rng, int L, int num_roads, td_map *out)
 {
-    if (L < 4 || L > TD_MAX_L || num_roads > TD_ROADS || !out) return TD_E_INVALID;
-    LegacyStream rng(seed, budget > 0 ? budget : 100000);
     try {
         if (num_roads <= 0) num_roads = rng.randint(1, TD_ROADS + 1);   // TDGymBasic.py:42
         RoadBuilder b(rng, L);
@@ -268,11 +277,27 @@ int generate_one(uint32_t seed, int L, int num_roads, int budget, td_map *out)
     }
 }
 
+int generate_one(uint32_t seed, int L, int num_roads, int budget, td_map *out)
+{
+    if (L < 4 || L > TD_MAX_L || num_roads > TD_ROADS || !out) return TD_E_INVALID;
+    LegacyStream rng(seed, budget > 0 ? budget : 100000);
+    return generate_from(rng, L, num_roads, out);
+}
+
 } // namespace
 
 extern "C" int td_mapgen(uint32_t seed, int map_size, int num_roads, int budget, td_map *out)
 {
     return generate_one(seed, map_size, num_roads, budget, out);
+}
+
+extern "C" int td_mapgen_stream(uint32_t *state625, int map_size, int num_roads, int budget, td_map *out)
+{
+    if (!state625 || map_size < 4 || map_size > TD_MAX_L || num_roads > TD_ROADS || !out) return TD_E_INVALID;
+    LegacyStream rng(state625, budget > 0 ? budget : 100000);
+    int rc = generate_from(rng, map_size, num_roads, out);
+    rng.save(state625);
+    return rc;
 }
 
 extern "C" int td_mapgen_batch(uint32_t *seeds, int n, int map_size, int num_roads, int budget,

@@ -85,7 +85,8 @@ class TdError(RuntimeError):
 
 _lib = None
 
-EXPORTS = ["td_abi_version", "td_last_error", "td_default_config", "td_mapgen", "td_mapgen_batch", "td_create",
+EXPORTS = ["td_abi_version", "td_last_error", "td_default_config", "td_mapgen", "td_mapgen_stream",
+           "td_mapgen_batch", "td_seed_opponent_python", "td_create",
            "td_destroy", "td_set_config", "td_get_layout", "td_upload_maps", "td_set_map_stride", "td_reset",
            "td_seed_opponent", "td_set_difficulty", "td_step", "td_observe", "td_step_host", "td_get_state",
            "td_set_state", "td_get_opponent", "td_get_stats", "td_reset_stats"]
@@ -103,6 +104,8 @@ def lib():
         L.td_last_error.argtypes = [C.c_void_p]
         L.td_default_config.restype = None
         L.td_mapgen.argtypes = [C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.td_mapgen_stream.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.td_seed_opponent_python.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.td_mapgen_batch.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p]
         L.td_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
@@ -238,6 +241,11 @@ class Engine(object):
         states = np.ascontiguousarray(states, dtype=np.uint32)
         assert states.ndim == 2 and states.shape[1] == 625
         self._check(self._lib.td_seed_opponent(self._h, states.ctypes.data, int(first_env), states.shape[0]))
+
+    def seed_opponent_python(self, seeds, first_env=0):
+        """Env i gets the generator state of CPython's random.seed(int(seeds[i]))."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32).reshape(-1)
+        self._check(self._lib.td_seed_opponent_python(self._h, seeds.ctypes.data, int(first_env), seeds.shape[0]))
 
     def get_opponent(self, first_env=0, n=None):
         n = self.n_envs - first_env if n is None else n

@@ -24,6 +24,21 @@ def generate(seed, map_size, num_roads=0, budget=DEFAULT_BUDGET):
     return m if rc == 1 else None
 
 
+def generate_from_stream(rs, map_size, num_roads=0, budget=DEFAULT_BUDGET):
+    """Draw one map from a live numpy.random.RandomState (advanced in place), like TDGymBasic.reset does
+    with self.np_random.  Returns a TdMap or None (stream advanced either way)."""
+    st = rs.get_state()
+    buf = np.empty(625, dtype=np.uint32)
+    buf[:624] = st[1]
+    buf[624] = st[2]
+    m = engine.TdMap()
+    rc = engine.lib().td_mapgen_stream(buf.ctypes.data, int(map_size), int(num_roads), int(budget), C.byref(m))
+    if rc < 0:
+        raise engine.TdError(rc, "td_mapgen_stream failed")
+    rs.set_state((st[0], buf[:624].copy(), int(buf[624]), 0, 0.0))
+    return m if rc == 1 else None
+
+
 def generate_batch(seeds, map_size, num_roads=0, budget=DEFAULT_BUDGET, skip_invalid=True, threads=None):
     """Generate len(seeds) maps on host threads.
 

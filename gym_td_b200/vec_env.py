@@ -1,0 +1,194 @@
+"""TDVecEnv: N independent gym-TD instances advanced in lockstep on one B200.
+
+The batched counterpart of the reference's `gym.vector.AsyncVectorEnv([make_fn] * n)` use
+(train/main.py:345): same per-env semantics as TDDefense / TDAttack / TDMulti.step, a leading
+env dimension on every tensor, finished envs restarted in place on the next map of the pool.
+All tensors live on the GPU; `step()` launches one fused kernel and returns views of
+pre-allocated output tensors (valid until the next step).
+
+Seeding contract: env with global index g = env_offset + i uses the first valid
+map seed >= seed + g (numpy RandomState stream, num_roads drawn first) and a scripted-opponent
+generator in the state of CPython's random.seed(seed + g), which keeps running across episodes
+like the reference's global `random` module does.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import mapgen, params
+
+
+class TDVecEnv(object):
+    def __init__(self, kind, map_size, num_envs, seed=0, device=0, difficulty=1, auto_reset=True, env_offset=0,
+                 n_maps=None, scripted_opponent=True, multi_action=None, cfg=None, mapgen_threads=None):
+        if kind not in E.KINDS:
+            raise ValueError("kind must be one of %r" % (sorted(E.KINDS),))
+        self.kind, self.map_size, self.num_envs = kind, int(map_size), int(num_envs)
+        self.device = torch.device("cuda", device)
+        self.auto_reset = bool(auto_reset)
+        self.multi_action = params.hyper_parameters.allow_multiple_actions if multi_action is None else bool(multi_action)
+        if kind == "atk":
+            self.multi_action = False
+        self.engine = E.Engine(kind, map_size, num_envs, device=device, cfg=cfg)
+        n_maps = self.num_envs if n_maps is None else int(n_maps)
+        base = (int(seed) + int(env_offset)) & 0xFFFFFFFF
+        seeds = (np.arange(n_maps, dtype=np.uint64) + base).astype(np.uint32)
+        maps, self.map_seeds, _ = mapgen.generate_batch(seeds, map_size, threads=mapgen_threads)
+        self.engine.upload_maps(maps)
+        self.engine.set_map_stride(1)
+        self.num_roads = np.array([maps[i].num_roads for i in range(n_maps)], dtype=np.int32)
+        if scripted_opponent and kind != "2p":
+            self.engine.set_difficulty(difficulty)
+            self.engine.seed_opponent_python((np.arange(num_envs, dtype=np.uint64) + base).astype(np.uint32))
+        N, L, dev = self.num_envs, self.map_size, self.device
+        self.obs = torch.empty((N, E.NCH, L, L), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(N, dtype=torch.float64, device=dev)
+        self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.win = torch.zeros(N, dtype=torch.int8, device=dev)
+        self._allow = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self.fail_def = torch.zeros(N, dtype=torch.int32, device=dev)
+        self.fail_atk = torch.zeros((N, 4), dtype=torch.int32, device=dev)
+        self.real_atk = torch.zeros((N, E.ROADS, E.CLUSTER), dtype=torch.int64, device=dev)
+        self.real_def = torch.zeros((N, 6, L, L) if self.multi_action else (N,), dtype=torch.int64, device=dev)
+        self._host = None
+
+    # -- spaces-like metadata -------------------------------------------------------------------
+    @property
+    def observation_shape(self):
+        return (self.num_envs, E.NCH, self.map_size, self.map_size)
+
+    def empty_action(self):
+        """Batched TD*.empty_action() (TDDefense.py:28-32, TDAttack.py:24-25, TDMulti.py:30-40)."""
+        N, L = self.num_envs, self.map_size
+        d = (torch.zeros((N, 6, L, L), dtype=torch.int64, device=self.device) if self.multi_action
+             else torch.full((N,), 6 * L * L, dtype=torch.int64, device=self.device))
+        a = torch.full((N, E.ROADS, E.CLUSTER), E.NT, dtype=torch.int64, device=self.device)
+        return {"def": d, "atk": a, "2p": {"Attacker": a, "Defender": d}}[self.kind]
+
+    # -- core -----------------------------------------------------------------------------------
+    def reset(self, mask=None, map_ids=None):
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        if mask is not None:
+            mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        if map_ids is not None:
+            map_ids = map_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        self.engine.reset(mask=mask, map_ids=map_ids, obs=self.obs, stream=s)
+        return self.obs
+
+    def _split(self, action):
+        if self.kind == "def":
+            return action, None
+        if self.kind == "atk":
+            return None, action
+        return action["Defender"], action["Attacker"]
+
+    def _io(self, d, a, opponent=None):
+        return E.Engine.make_io(def_action=d, atk_action=a, opponent=opponent, multi_action=self.multi_action,
+                                auto_reset=self.auto_reset, obs=self.obs, reward=self.reward, done=self._done,
+                                win=self.win, allow_next=self._allow, real_def=self.real_def,
+                                real_atk=self.real_atk, fail_def=self.fail_def, fail_atk=self.fail_atk)
+
+    def _check(self, d, a):
+        N, L = self.num_envs, self.map_size
+        if d is not None:
+            want = (N, 6, L, L) if self.multi_action else (N,)
+            if tuple(d.shape) != want or d.dtype != torch.int64 or not d.is_cuda or not d.is_contiguous():
+                raise AssertionError("defender action must be a contiguous CUDA int64 tensor of shape %r" % (want,))
+        if a is not None:
+            want = (N, E.ROADS, E.CLUSTER)
+            if tuple(a.shape) != want or a.dtype != torch.int64 or not a.is_cuda or not a.is_contiguous():
+                raise AssertionError("attacker action must be a contiguous CUDA int64 tensor of shape %r" % (want,))
+
+    def step(self, action, opponent=None):
+        """One lockstep step.  Returns (obs, reward, done, info) -- tensors with a leading env dim."""
+        d, a = self._split(action)
+        self._check(d, a)
+        self.engine.step(self._io(d, a, opponent), torch.cuda.current_stream(self.device).cuda_stream)
+        return self.obs, self.reward, self._done.view(torch.bool), self.info()
+
+    def info(self):
+        allow = self._allow
+        inf = {"Win": self.win}
+        if self.kind == "def":
+            inf.update(RealAction=self.real_def, AllowNextMove=(allow & 1).bool(), FailCode=self.fail_def)
+        elif self.kind == "atk":
+            inf.update(RealAction=self.real_atk, AllowNextMove=(allow & 2).bool(), FailCode=self.fail_atk)
+        else:
+            inf.update(RealAction={"Attacker": self.real_atk, "Defender": self.real_def},
+                       AllowNextMove={"Attacker": (allow & 2).bool(), "Defender": (allow & 1).bool()},
+                       FailCode={"Attacker": self.fail_atk, "Defender": self.fail_def})
+        return inf
+
+    # -- host-buffer path (what a numpy-facing gym caller uses) ------------------------------------
+    def _host_buffers(self):
+        if self._host is None:
+            N = self.num_envs
+            pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
+            h = dict(reward=pin(self.reward), done=pin(self._done), win=pin(self.win), allow=pin(self._allow),
+                     fail_def=pin(self.fail_def), fail_atk=pin(self.fail_atk), real_atk=pin(self.real_atk),
+                     real_def=pin(self.real_def), obs=None)
+            h["def_dev"] = torch.zeros_like(self.real_def)
+            h["atk_dev"] = torch.zeros_like(self.real_atk)
+            self._host = h
+        return self._host
+
+    def step_host(self, action, want_obs=False):
+        """Host in, host out through td_step_host: `action` are pinned CPU int64 tensors; the small outputs
+        (and the observation when want_obs) are copied back and the stream is synchronised."""
+        h = self._host_buffers()
+        d, a = self._split(action)
+        if want_obs and h["obs"] is None:
+            h["obs"] = torch.empty(self.obs.shape, dtype=torch.float32).pin_memory()
+        io = self._io(h["def_dev"] if d is not None else None, h["atk_dev"] if a is not None else None)
+        hio = E.TdHostIO()
+        hio.def_action_host = d.data_ptr() if d is not None else None
+        hio.atk_action_host = a.data_ptr() if a is not None else None
+        hio.obs_host = h["obs"].data_ptr() if want_obs else None
+        hio.reward_host, hio.done_host, hio.win_host = h["reward"].data_ptr(), h["done"].data_ptr(), h["win"].data_ptr()
+        hio.allow_next_host = h["allow"].data_ptr()
+        if self.kind != "atk":
+            hio.real_def_host, hio.fail_def_host = h["real_def"].data_ptr(), h["fail_def"].data_ptr()
+        if self.kind != "def":
+            hio.real_atk_host, hio.fail_atk_host = h["real_atk"].data_ptr(), h["fail_atk"].data_ptr()
+        self.engine.step_host(io, hio, torch.cuda.current_stream(self.device).cuda_stream)
+        return h
+
+    def host_bytes_per_step(self, want_obs=False):
+        N, L = self.num_envs, self.map_size
+        h2d = 0
+        if self.kind != "atk":
+            h2d += self.real_def.numel() * 8
+        if self.kind != "def":
+            h2d += N * 24 * 8
+        d2h = N * (8 + 1 + 1 + 1)
+        if self.kind != "atk":
+            d2h += self.real_def.numel() * 8 + N * 4
+        if self.kind != "def":
+            d2h += N * 24 * 8 + N * 16
+        if want_obs:
+            d2h += N * E.NCH * L * L * 4
+        return h2d, d2h
+
+    # -- statistics -------------------------------------------------------------------------------
+    def stats(self):
+        s = self.engine.stats(torch.cuda.current_stream(self.device).cuda_stream)
+        if s["overflow_envs"]:
+            raise E.TdError(-5, "%d env(s) exceeded the tower/enemy capacity; their results are invalid"
+                            % s["overflow_envs"])
+        return s
+
+    def allreduce_stats(self):
+        """Episode statistics summed over all ranks (NCCL all_reduce when torch.distributed is up)."""
+        s = self.stats()
+        keys = ["return_sum", "episodes", "length_sum", "wins", "kills", "leaks", "steps"]
+        v = torch.tensor([float(s[k]) for k in keys], dtype=torch.float64, device=self.device)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(v, op=dist.ReduceOp.SUM)
+        out = {k: (float(x) if k == "return_sum" else int(x)) for k, x in zip(keys, v.tolist())}
+        return out
+
+    def close(self):
+        self.engine.close()

@@ -194,6 +194,9 @@ void td_default_config(td_config *cfg);
  * Returns 1 if the seed is valid, 0 if the reference generator would raise or exceed
  * `budget` randint calls (seed-skip rule), <0 on error. */
 int td_mapgen(uint32_t seed, int map_size, int num_roads, int budget, td_map *out);
+/* same generator on an explicit stream: state625 = RandomState.get_state() key (624 words) + position,
+ * updated in place, so successive resets keep drawing from one stream like self.np_random does. */
+int td_mapgen_stream(uint32_t *state625_inout, int map_size, int num_roads, int budget, td_map *out);
 /* n seeds in parallel on `threads` host threads; valid_out[i] as above. first-valid search:
  * if skip_invalid != 0, seed i is advanced (s <- s+1) until valid and seeds_inout[i] is updated. */
 int td_mapgen_batch(uint32_t *seeds_inout, int n, int map_size, int num_roads, int budget,
@@ -216,6 +219,8 @@ int td_reset(td_handle *h, const uint8_t *mask_dev, const int32_t *map_ids_dev, 
 /* seed the per-env scripted-opponent generators: states_host is [n_envs][625] uint32
  * (624 MT19937 words + position, i.e. random.Random(s).getstate()[1]). */
 int td_seed_opponent(td_handle *h, const uint32_t *states_host, int first_env, int n);
+/* same, from integer seeds: env i gets the state of CPython's random.seed(seeds_host[i]) (0 <= seed < 2^32) */
+int td_seed_opponent_python(td_handle *h, const uint32_t *seeds_host, int first_env, int n);
 /* scripted opponent level (difficulty kwarg of TDDefense/TDAttack); default 1 */
 int td_set_difficulty(td_handle *h, int difficulty);
 

@@ -1,0 +1,101 @@
+"""CPU baselines for bench.py (TEST INFRASTRUCTURE: the checker / reported baseline, never the product).
+
+reference leg: the UNMODIFIED Python reference (baseline/_ref or /root/reference, through the gym
+stub), one process per host core, each stepping its own env instances -- the stand-in for the
+reference's gym.vector.AsyncVectorEnv usage (train/main.py:345).
+port leg: the C restatement (oracle/td_oracle.c), one thread per core (ctypes releases the GIL).
+"""
+import multiprocessing as mp
+import os
+import random
+import threading
+import time
+
+import numpy as np
+
+
+def _ref_worker(args):
+    kind, L, n_steps, seed = args
+    import warnings
+    warnings.simplefilter("ignore")
+    np.seterr(all="ignore")
+    from oracle import ref_harness as RH
+    seed, env = RH.first_valid_seed(kind, L, seed)
+    random.seed(seed)
+    rs = np.random.RandomState(seed)
+    n_act = 6 * L * L + 1
+    acts = rs.randint(n_act, size=n_steps)
+    atk = rs.randint(0, 5, size=(64, 3, 8)).astype(np.int64)
+    done_steps = 0
+    t0 = time.perf_counter()
+    for i in range(n_steps):
+        if kind == "def":
+            _, _, done, _ = env.step(int(acts[i]))
+        elif kind == "atk":
+            _, _, done, _ = env.step(atk[i & 63])
+        else:
+            _, _, done, _ = env.step({"Attacker": atk[i & 63], "Defender": int(acts[i])})
+        done_steps += 1
+        if done:
+            seed, env = RH.first_valid_seed(kind, L, seed + 1)
+    return done_steps, time.perf_counter() - t0
+
+
+class ReferencePool(object):
+    """Persistent process pool so that repeated bounded samples do not pay the import cost."""
+
+    def __init__(self, workers=None):
+        self.workers = workers or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.workers)
+        self.calls = 0
+
+    def run(self, kind, L, steps_per_worker):
+        self.calls += 1
+        args = [(kind, L, steps_per_worker, 100000 * self.calls + 1000 * w) for w in range(self.workers)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_ref_worker, args)
+        wall = time.perf_counter() - t0
+        return sum(r[0] for r in res), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_available():
+    from oracle import ref_loader
+    return ref_loader.available()
+
+
+def run_port(L, steps_per_thread, threads=None):
+    """C oracle, TDDefense Discrete + scripted attacker + observation every step; returns (steps, wall)."""
+    import ctypes as C
+    from oracle import td_oracle as TO
+    from gym_td_b200 import mapgen
+    threads = threads or os.cpu_count() or 1
+    lib = TO.lib()
+    envs, bufs = [], []
+    for t in range(threads):
+        m = None
+        s = 5000 + 17 * t
+        while m is None:
+            m = mapgen.generate(s, L)
+            s += 1
+        p = mapgen.planes(m)
+        bits = (p["road"][0] | (p["road"][1] << 1) | (p["road"][2] << 2) | (p["road"][3] << 3)).astype(np.uint8)
+        o = TO.OracleEnv()
+        o.init_from_planes(L, p["num_roads"], p["start"], p["end"], bits, p["dist"], p["dir"])
+        o.set_pyrand(random.Random(s).getstate())
+        envs.append(o)
+        bufs.append(np.empty(45 * L * L, dtype=np.float32))
+
+    def work(i):
+        lib.tdo_bench_def(C.byref(envs[i].e), int(steps_per_thread), 12345 + i, bufs[i].ctypes.data)
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(threads)]
+    t0 = time.perf_counter()
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    return threads * steps_per_thread, time.perf_counter() - t0

@@ -866,3 +866,37 @@ void tdo_multi_step_multi(tdo_env *e, const int64_t *atk_action, const int64_t *
     decode_multi(e, def_action, real_def);
     finish_def(e, o);
 }
+
+/* ------------------------------------------------------------------ cpu_baseline "port" leg */
+
+static void board_restart(tdo_env *e)
+{
+    /* TDGymBasic.reset on the same map: fresh TDBoard state (TDBoard.py:63-79) */
+    const int cells = e->L * e->L;
+    for (int c = 0; c < cells; ++c) e->map6[c] = (e->road[c] & 1) ? 1 : 0;
+    memset(e->enemy_LP, 0, sizeof(e->enemy_LP));
+    e->cost_def = e->cfg.defender_init_cost;
+    e->cost_atk = e->cfg.attacker_init_cost;
+    e->base_LP = e->cfg.base_LP;
+    e->steps = 0;
+    e->progress = 0.;
+    e->n_towers = e->n_enemies = 0;
+    e->attacker_cd = e->defender_cd = 0;
+    e->fail_code = TDO_SUCCESS;
+}
+
+double tdo_bench_def(tdo_env *e, int n_steps, uint64_t s, float *obs_buf)
+{
+    const int64_t n_act = (int64_t)e->L * e->L * 6 + 1;
+    double acc = 0.;
+    tdo_step_out o;
+    if (!s) s = 88172645463325252ull;
+    for (int i = 0; i < n_steps; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        tdo_def_step(e, (int64_t)(s % (uint64_t)n_act), 1, 0, &o);
+        tdo_get_states(e, obs_buf);
+        acc += o.reward + obs_buf[11 * e->L * e->L];
+        if (o.done) board_restart(e);
+    }
+    return acc;
+}

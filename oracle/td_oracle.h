@@ -162,6 +162,11 @@ void tdo_multi_step(tdo_env *e, const int64_t *atk_action, int64_t def_action, t
 void tdo_multi_step_multi(tdo_env *e, const int64_t *atk_action, const int64_t *def_action,
                           int64_t *real_def, tdo_step_out *o);
 
+/* cpu_baseline "port" leg: run n env-steps of TDDefense (Discrete, uniform random actions from a
+ * xorshift stream, scripted attacker lv1 on e->pyrand), building the observation every step and
+ * restarting the episode on the same map when done.  Returns a checksum so the work is not elided. */
+double tdo_bench_def(tdo_env *e, int n_steps, uint64_t action_seed, float *obs_buf);
+
 /* RNG helpers (exposed for tests) */
 void tdo_mt_set(tdo_mt *m, const uint32_t *key624, int pos);
 void tdo_mt_seed_numpy(tdo_mt *m, uint32_t seed);             /* RandomState(seed) */

@@ -113,6 +113,8 @@ def lib():
         L.tdo_mt_next.restype = C.c_uint32
         L.tdo_py_randbelow.restype = C.c_uint32
         L.tdo_def_step.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p]
+        L.tdo_bench_def.restype = C.c_double
+        L.tdo_bench_def.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
         L.tdo_multi_step.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         _lib = L
     return _lib
