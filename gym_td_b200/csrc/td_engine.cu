@@ -183,6 +183,33 @@ static void fill_params(const td_handle *h, StepParams &p)
 static int grid_of(const td_handle *h) { return (h->n_envs + kWarpsPerCta - 1) / kWarpsPerCta; }
 static size_t smem_of(const td_handle *h) { return (size_t)kWarpsPerCta * h->smem_per_warp; }
 
+// The step kernel is specialised on (env kind, multi-action) x (board size, enemy chunks): 10x10 boards hold at
+// most 32 live enemies (one per lane), larger boards 64; other sizes take the run-time-size variant.
+static int step_variant(int kind, bool multi)
+{
+    return kind == TD_KIND_DEF ? (multi ? 1 : 0) : kind == TD_KIND_ATK ? 2 : (multi ? 4 : 3);
+}
+
+template <int CELLS, int NCHUNK, typename F> static cudaError_t for_each_kind(F f)
+{
+    cudaError_t e;
+    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK>)) != cudaSuccess) return e;
+    return f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK>);
+}
+
+template <typename F> static cudaError_t for_each_step_kernel(const td_handle *h, F f)
+{
+    switch (h->L) {
+    case 10: return for_each_kind<100, 1>(f);
+    case 20: return for_each_kind<400, 2>(f);
+    case 30: return for_each_kind<900, 2>(f);
+    default: return for_each_kind<0, 2>(f);
+    }
+}
+
 template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
 {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -222,11 +249,7 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     if ((e = cudaSetDevice(device)) != cudaSuccess) { h->err = cudaGetErrorString(e); return bail(TD_E_CUDA); }
     size_t smem = smem_of(h);
     if (smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
-    if ((e = allow_smem(td_step_kernel<TD_KIND_DEF, false>, smem)) != cudaSuccess ||
-        (e = allow_smem(td_step_kernel<TD_KIND_DEF, true>, smem)) != cudaSuccess ||
-        (e = allow_smem(td_step_kernel<TD_KIND_ATK, false>, smem)) != cudaSuccess ||
-        (e = allow_smem(td_step_kernel<TD_KIND_2P, false>, smem)) != cudaSuccess ||
-        (e = allow_smem(td_step_kernel<TD_KIND_2P, true>, smem)) != cudaSuccess ||
+    if ((e = for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, smem); })) != cudaSuccess ||
         (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel, smem)) != cudaSuccess) {
         h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
@@ -476,15 +499,12 @@ extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
     const int grid = grid_of(h), block = kWarpsPerCta * 32;
     const size_t smem = smem_of(h);
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->kind == TD_KIND_DEF) {
-        if (io->multi_action) td_step_kernel<TD_KIND_DEF, true><<<grid, block, smem, s>>>(p);
-        else td_step_kernel<TD_KIND_DEF, false><<<grid, block, smem, s>>>(p);
-    } else if (h->kind == TD_KIND_ATK) {
-        td_step_kernel<TD_KIND_ATK, false><<<grid, block, smem, s>>>(p);
-    } else {
-        if (io->multi_action) td_step_kernel<TD_KIND_2P, true><<<grid, block, smem, s>>>(p);
-        else td_step_kernel<TD_KIND_2P, false><<<grid, block, smem, s>>>(p);
-    }
+    const int want = step_variant(h->kind, io->multi_action != 0);
+    int seen = 0;
+    for_each_step_kernel(h, [&](auto kernel) {
+        if (seen++ == want) kernel<<<grid, block, smem, s>>>(p);
+        return cudaSuccess;
+    });
     TD_CUDA(h, cudaGetLastError());
     h->steps += h->n_envs;
     return TD_OK;

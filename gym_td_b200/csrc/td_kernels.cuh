@@ -93,7 +93,7 @@ struct Ctx {
     uint8_t *cells;
     uint8_t *dist;
     uint8_t *scratch;          // >= 512 bytes (+128 byte index scratch behind it)
-    int lane, L, ncells, cells_pad;
+    int lane, L, ncells, cells_pad, ecap;
     // uniform copies of hot header fields (identical in all lanes)
     double cost_def, cost_atk;
     int nt, ne, base_LP, steps, def_cd, atk_cd, fail, flags;
@@ -108,6 +108,21 @@ __device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16,
     int4 *d = reinterpret_cast<int4 *>(dst);
     const int4 *s = reinterpret_cast<const int4 *>(src);
     for (int q = lane; q < n16; q += 32) d[q] = s[q];
+}
+
+// global -> shared, 16 bytes per lane per instruction, asynchronous (LDGSTS): every segment of a stage
+// is in flight at once and no register is held while the data travels.
+__device__ __forceinline__ void async_copy16(void *smem_dst, const void *gmem_src, int n16, int lane)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const char *s = reinterpret_cast<const char *>(gmem_src);
+    for (int q = lane; q < n16; q += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * q), "l"(s + 16 * q) : "memory");
+}
+__device__ __forceinline__ void async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
 }
 
 __device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, const StepParams &p)
@@ -125,13 +140,14 @@ __device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, const StepParam
     w.L = p.L;
     w.ncells = p.cells;
     w.cells_pad = p.cells_pad;
+    w.ecap = TD_CAP_ENEMIES;
     w.mt = nullptr;
     w.win = 0; w.mt_pos = 0; w.win_k = 0; w.win_n = 0;
 }
 
 __device__ __forceinline__ void load_static_map(Ctx &w, const StepParams &p, int map_id)
 {
-    warp_copy16(w.mh, p.maps + (size_t)map_id * p.map_bytes, p.map_bytes >> 4, w.lane);
+    async_copy16(w.mh, p.maps + (size_t)map_id * p.map_bytes, p.map_bytes >> 4, w.lane);
 }
 
 __device__ __forceinline__ void pull_header(Ctx &w)
@@ -167,17 +183,77 @@ __device__ __forceinline__ void push_header(Ctx &w)
     }
 }
 
-// Stage one env: header + map6 first (independent), then the live prefixes and the static map.
-__device__ __forceinline__ void load_env(Ctx &w, const StepParams &p, const uint8_t *rec)
+// ------------------------------------------------------------------------------------------------
+// CPython-compatible MT19937 consumer (random.Random): one tempered window of <= 32 words per fill
+
+// Regenerate the 624 words in place.  mt[k] = mt[(k+397)%624] ^ f(mt[k], mt[k+1]); chunks of 32 words in
+// ascending order keep every operand in the state (old / new) the sequential algorithm sees.
+__device__ __noinline__ void mt_twist(uint32_t *mt, int lane)
 {
-    if (w.lane < 4) reinterpret_cast<int4 *>(w.hdr)[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
-    warp_copy16(w.map6, rec + kOffMap6, p.cells_pad >> 4, w.lane);
+#pragma unroll 1
+    for (int base = 0; base < kMtWords; base += 32) {
+        const int k = base + lane;
+        uint32_t v = 0;
+        if (k < kMtWords - 1) {
+            uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1] & 0x7fffffffu);
+            v = mt[k < 227 ? k + 397 : k - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        __syncwarp();
+        if (k < kMtWords - 1) mt[k] = v;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
+        mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
     __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y)
+{
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// Load the next <= 32 words (untempered) into the lanes; a no-op when the state needs a twist first.
+__device__ __forceinline__ void mt_fill_window(Ctx &w)
+{
+    int n = kMtWords - w.mt_pos;
+    w.win_n = n < 32 ? (n < 0 ? 0 : n) : 32;
+    w.win_k = 0;
+    w.win = w.lane < w.win_n ? w.mt[w.mt_pos + w.lane] : 0u;
+}
+
+__device__ __forceinline__ uint32_t mt_next(Ctx &w)
+{
+    if (w.win_k == w.win_n) {
+        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane); w.mt_pos = 0; }
+        mt_fill_window(w);
+    }
+    uint32_t r = mt_temper(__shfl_sync(kFull, w.win, w.win_k));
+    ++w.win_k;
+    ++w.mt_pos;
+    return r;
+}
+
+// Stage one env: header + map6 first (independent), then the live prefixes and the static map.
+__device__ __forceinline__ void load_env(Ctx &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base = nullptr)
+{
+    async_copy16(w.hdr, rec, kHdrBytes >> 4, w.lane);
+    async_copy16(w.map6, rec + kOffMap6, p.cells_pad >> 4, w.lane);
+    async_wait_all();
     pull_header(w);
-    warp_copy16(w.tw, rec + kOffTowers, w.nt, w.lane);                       // 16 B per tower
-    warp_copy16(w.en, rec + kOffEnemies, (w.ne * 3 + 1) >> 1, w.lane);        // 24 B per enemy
+    async_copy16(w.tw, rec + kOffTowers, w.nt, w.lane);                       // 16 B per tower
+    async_copy16(w.en, rec + kOffEnemies, (w.ne * 3 + 1) >> 1, w.lane);        // 24 B per enemy
     load_static_map(w, p, w.hdr->map_id);
-    __syncwarp();
+    if (mt_base) {                                                            // scripted-opponent words ride along
+        w.mt = mt_base;
+        mt_fill_window(w);
+    }
+    async_wait_all();
 }
 
 __device__ __forceinline__ void store_env(Ctx &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
@@ -196,7 +272,7 @@ __device__ __forceinline__ void reset_env(Ctx &w, const StepParams &p, int map_i
     if (reload_map) {
         __syncwarp();
         load_static_map(w, p, map_id);
-        __syncwarp();
+        async_wait_all();
     }
     for (int q = w.lane; q < (p.cells_pad >> 2); q += 32) {
         uint32_t c4 = reinterpret_cast<const uint32_t *>(w.cells)[q];
@@ -218,62 +294,6 @@ __device__ __forceinline__ void reset_env(Ctx &w, const StepParams &p, int map_i
         w.hdr->ep_leaks = 0;
     }
     __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------------
-// CPython-compatible MT19937 consumer (random.Random): one tempered window of <= 32 words per fill
-
-__device__ __forceinline__ void mt_twist(uint32_t *mt, int lane)
-{
-    // mt[k] = mt[k+397] ^ f(mt[k], mt[k+1]); three dependency-free phases + the last word
-    auto f = [](uint32_t a, uint32_t b) {
-        uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-        return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    };
-    uint32_t v[8];
-    // phase A: k in [0, 227) reads old mt[k], mt[k+1], mt[k+397]
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < 227) v[i] = mt[k + 397] ^ f(mt[k], mt[k + 1]); }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int k = lane + 32 * i; if (k < 227) mt[k] = v[i]; }
-    __syncwarp();
-    // phase B: k in [227, 454) reads new mt[k-227], old mt[k], mt[k+1]
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int k = 227 + lane + 32 * i; if (k < 454) v[i] = mt[k - 227] ^ f(mt[k], mt[k + 1]); }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int k = 227 + lane + 32 * i; if (k < 454) mt[k] = v[i]; }
-    __syncwarp();
-    // phase C: k in [454, 623)
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int k = 454 + lane + 32 * i; if (k < 623) v[i] = mt[k - 227] ^ f(mt[k], mt[k + 1]); }
-    __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { int k = 454 + lane + 32 * i; if (k < 623) mt[k] = v[i]; }
-    __syncwarp();
-    if (lane == 0) mt[623] = mt[396] ^ f(mt[623], mt[0]);
-    __syncwarp();
-}
-
-__device__ __forceinline__ uint32_t mt_next(Ctx &w)
-{
-    if (w.win_k == w.win_n) {
-        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane); w.mt_pos = 0; }
-        int n = kMtWords - w.mt_pos;
-        w.win_n = n < 32 ? n : 32;
-        uint32_t y = w.lane < w.win_n ? w.mt[w.mt_pos + w.lane] : 0u;
-        y ^= y >> 11;
-        y ^= (y << 7) & 0x9d2c5680u;
-        y ^= (y << 15) & 0xefc60000u;
-        y ^= y >> 18;
-        w.win = y;
-        w.win_k = 0;
-    }
-    uint32_t r = __shfl_sync(kFull, w.win, w.win_k);
-    ++w.win_k;
-    ++w.mt_pos;
-    return r;
 }
 
 // random._randbelow_with_getrandbits(n), 1 <= n < 2^31
@@ -457,7 +477,7 @@ __device__ __forceinline__ void decode_multi(Ctx &w, const long long *act, long 
 
 __device__ __forceinline__ void append_enemy(Ctx &w, int t, int lv, int start)
 {
-    if (w.ne >= TD_CAP_ENEMIES) { w.flags |= 1; return; }
+    if (w.ne >= w.ecap) { w.flags |= 1; return; }
     if (w.lane == 0) {
         td_enemy_rec &e = w.en[w.ne];
         e.LP = cc.enemy_LP[t][lv];
@@ -476,7 +496,7 @@ __device__ __forceinline__ bool summon_cluster(Ctx &w, int road, long long &mine
     const int start = w.mh->start[road];
     const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
     bool tried = false, summoned = false;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < TD_CLUSTER; ++k) {
         long long t = __shfl_sync(kFull, mine, lane_base + k);
         if (t < 0 || t >= TD_NTYPES) continue;               // 4 == enemy_types: empty slot
@@ -495,11 +515,33 @@ __device__ __forceinline__ bool summon_cluster(Ctx &w, int road, long long &mine
     return true;
 }
 
-// scripted attacker of the defender env: 8 x type t on one road (TDGymBasic.py:95-108)
+// scripted attacker of the defender env: 8 x type t on one road (TDGymBasic.py:95-108 -> TDBoard.py:199-224).
+// All eight slots cost the same, so the first unaffordable slot ends the cluster; the summoned enemies are
+// appended by eight lanes at once.
 __device__ __forceinline__ void summon_uniform(Ctx &w, int t, int road)
 {
-    long long mine = t;
-    summon_cluster(w, road, mine, 0);   // every lane holds t, so any lane_base works
+    const int start = w.mh->start[road];
+    const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
+    const double cost = cc.enemy_cost[t][lv];
+    int n = 0;
+#pragma unroll 1
+    for (int k = 0; k < TD_CLUSTER; ++k) {
+        if (w.cost_atk < cost) break;
+        w.cost_atk = __dsub_rn(w.cost_atk, cost);
+        ++n;
+    }
+    w.fail = n == 0 ? TD_FC_COST_SHORTAGE : TD_FC_SUCCESS;
+    if (n > w.ecap - w.ne) { w.flags |= 1; n = w.ecap - w.ne; }
+    if (w.lane < n) {
+        td_enemy_rec &e = w.en[w.ne + w.lane];
+        e.LP = cc.enemy_LP[t][lv];
+        e.margin = 0.0;
+        e.loc = (uint16_t)start;
+        e.type_lv = (uint8_t)(t | (lv << 2));
+        e.slowdown = 0;
+    }
+    w.ne += n;
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -576,6 +618,7 @@ struct EnemyRegs {
     bool valid;
 };
 
+template <int NCHUNK>
 __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_out)
 {
     const int L = w.L, lane = w.lane;
@@ -584,15 +627,14 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
     const double progress = (double)w.steps / (double)cc.max_steps;
 
     const int ne = w.ne, nt = w.nt;
-    const int nchunk = (ne + 31) >> 5;                       // 0, 1 or 2
-    EnemyRegs E[2];
+    EnemyRegs E[NCHUNK];
     double *keys = reinterpret_cast<double *>(w.scratch);    // [64]
     uint8_t *erow = w.scratch + 512, *ecol = w.scratch + 576;  // [64] each
 
     // ---- load enemies into registers, sort key = dist - margin (TDBoard.py:305)
     bool unsorted = false;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NCHUNK; ++k) {
         int e = lane + 32 * k;
         E[k].valid = e < ne;
         if (E[k].valid) {
@@ -603,7 +645,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
     }
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NCHUNK; ++k) {
         int e = lane + 32 * k;
         bool inv = E[k].valid && e > 0 && keys[e - 1] > keys[e];
         unsorted = unsorted || inv;
@@ -611,18 +653,20 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
     unsorted = __any_sync(kFull, unsorted);
     if (unsorted) {
         // stable rank = #(key smaller) + #(equal key, earlier position)
-        int rank[2] = {0, 0};
+        int rank[NCHUNK];
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) rank[k] = 0;
         for (int j = 0; j < ne; ++j) {
             double kj = keys[j];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
+            for (int k = 0; k < NCHUNK; ++k) {
                 int e = lane + 32 * k;
                 if (E[k].valid) { double ke = keys[e]; rank[k] += (kj < ke || (kj == ke && j < e)) ? 1 : 0; }
             }
         }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 2; ++k)
+        for (int k = 0; k < NCHUNK; ++k)
             if (E[k].valid) {
                 td_enemy_rec &x = w.en[rank[k]];
                 x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
@@ -630,7 +674,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
             }
         __syncwarp();
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
+        for (int k = 0; k < NCHUNK; ++k) {
             int e = lane + 32 * k;
             if (E[k].valid) {
                 const td_enemy_rec &x = w.en[e];
@@ -639,7 +683,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
         }
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NCHUNK; ++k) {
         int e = lane + 32 * k;
         if (E[k].valid) {
             E[k].r = E[k].loc / L; E[k].c = E[k].loc - E[k].r * L;
@@ -687,11 +731,13 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
     __syncwarp();
 
     // ---- damage in tower order: lane = enemy (TDElements.py:19-28)
-    bool hit[2] = {false, false};
-    if (ne > 0) {
-        double defense[2];
+    bool hit[NCHUNK];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) defense[k] = E[k].valid ? cc.enemy_defense[E[k].tl & 3][E[k].tl >> 2] : 0.0;
+    for (int k = 0; k < NCHUNK; ++k) hit[k] = false;
+    if (ne > 0) {
+        double defense[NCHUNK];
+#pragma unroll
+        for (int k = 0; k < NCHUNK; ++k) defense[k] = E[k].valid ? cc.enemy_defense[E[k].tl & 3][E[k].tl >> 2] : 0.0;
         for (int t = 0; t < nt; ++t) {
             const int f = fire[t];
             if (f == 0xff) continue;
@@ -702,8 +748,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
             const int sp = cc.tower_splash[ty][lv];
             const int fr = erow[f], fc = ecol[f], v = vict[t];
 #pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                if (k >= nchunk) break;
+            for (int k = 0; k < NCHUNK; ++k) {
                 int e = lane + 32 * k;
                 bool h;
                 if (ty == 2) h = E[k].valid && max(abs(E[k].r - fr), abs(E[k].c - fc)) <= sp;
@@ -726,11 +771,11 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
     // ---- remove the killed, move the rest, remove the leaked (TDBoard.py:313-346)
     int kills = 0, leaks = 0, kept_before = 0;
     const int end = w.mh->end;
-    int newidx[2];
-    bool keep[2];
+    int newidx[NCHUNK];
+    bool keep[NCHUNK];
     __syncwarp();
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < NCHUNK; ++k) {
         bool killed = E[k].valid && hit[k] && !(E[k].LP > 0.0);
         bool leaked = false;
         if (E[k].valid && !killed) {
@@ -752,7 +797,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
         kept_before += __popc(bs);
     }
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
+    for (int k = 0; k < NCHUNK; ++k)
         if (keep[k]) {
             td_enemy_rec &x = w.en[newidx[k]];
             x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
@@ -800,9 +845,13 @@ __device__ __forceinline__ void fill_planes_scalar(float *o, int first_plane, in
     for (int q = lane; q < n_planes * cells; q += 32) __stcs(p + q, v);
 }
 
+// CELLS > 0: compile-time board size -> the observation is streamed as one flat run of float4 (every
+// lane busy, plane index by constant division, broadcast values from a 45-entry shared table).
+// CELLS == 0: run-time board size, plane by plane (also handles L*L not divisible by 4).
+template <int CELLS>
 __device__ __forceinline__ void write_obs(Ctx &w, float *o)
 {
-    const int lane = w.lane, cells = w.ncells;
+    const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells;
     const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
     const bool has_base = cc.base_LP >= 0;
     const float v5 = has_base ? (float)((double)w.base_LP / (double)cc.base_LP) : 1.f;
@@ -816,7 +865,48 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
         vb[t] = w.cost_def >= cc.tower_cost[t][0] ? 1.f : 0.f;
         vs[t] = (float)(w.cost_def / cc.enemy_cost[t][0] / 8.0);
     }
-    if (vec) {
+    if (CELLS > 0 && vec) {
+        constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
+        constexpr int N4 = TD_NCHANNELS * C4;
+        float *pv = reinterpret_cast<float *>(w.scratch) + 64;     // [48] plane values, behind ratio[64]
+        __syncwarp();
+        pv[lane] = 0.f;
+        if (lane < 16) pv[32 + lane] = 0.f;
+        __syncwarp();
+        if (lane == 0) {
+            pv[5] = v5; pv[11] = v11; pv[12] = v12; pv[13] = v13;
+#pragma unroll
+            for (int t = 0; t < TD_NTYPES; ++t) { pv[21 + t] = vb[t]; pv[41 + t] = vs[t]; }
+        }
+        __syncwarp();
+        float4 *o4 = reinterpret_cast<float4 *>(o);
+        const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells);
+        const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist);
+        const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6);
+#pragma unroll 4
+        for (int q = lane; q < N4; q += 32) {
+            const int pl = q / C4, i = q - pl * C4;
+            float4 v;
+            if ((0x420fu >> pl) & 1u) {                            // per-cell planes 0-3, 9, 14
+                if (pl < 4) {
+                    uchar4 c = cb[i];
+                    v = make_float4((float)((c.x >> pl) & 1), (float)((c.y >> pl) & 1),
+                                    (float)((c.z >> pl) & 1), (float)((c.w >> pl) & 1));
+                } else if (pl == 9) {
+                    uchar4 d = db[i];
+                    v = make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
+                                    __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd));
+                } else {
+                    uchar4 m = mb[i];
+                    v = make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f, m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f);
+                }
+            } else {
+                const float x = pv[pl];
+                v = make_float4(x, x, x, x);
+            }
+            __stcs(o4 + q, v);
+        }
+    } else if (vec) {
         const int c4 = cells >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells);
@@ -916,8 +1006,12 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
 
 extern __shared__ __align__(16) uint8_t td_smem[];
 
-template <int KIND, bool MULTI>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) td_step_kernel(const StepParams p)
+#ifndef TD_MIN_BLOCKS
+#define TD_MIN_BLOCKS 8
+#endif
+
+template <int KIND, bool MULTI, int CELLS, int NCHUNK>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const StepParams p)
 {
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;
@@ -925,13 +1019,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) td_step_kernel(const StepPa
     Ctx w;
     ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     uint8_t *rec = p.records + (size_t)env * p.record_bytes;
-    load_env(w, p, rec);
-    const int lane = w.lane;
     const td_step_io &io = p.io;
-    bool dirty = false;
     const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
                                  !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
-    if (device_opponent) w.mt = p.mt + (size_t)env * kMtWords;
+    w.ecap = 32 * NCHUNK;
+    load_env(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
+    const int lane = w.lane;
+    bool dirty = false;
 
     // cooldowns (TDDefense.py:38-39)
     w.atk_cd = max(w.atk_cd - 1, 0);
@@ -991,7 +1085,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) td_step_kernel(const StepPa
     __syncwarp();
 
     int kills, leaks;
-    double reward = board_step(w, kills, leaks);
+    double reward = board_step<NCHUNK>(w, kills, leaks);
     if (KIND == TD_KIND_ATK) reward = -reward;
 
     const bool has_base = cc.base_LP >= 0;
@@ -1039,7 +1133,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) td_step_kernel(const StepPa
         reset_env(w, p, next, true);
         dirty = true;
     }
-    if (io.obs_dev) write_obs(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells);
+    if (io.obs_dev) write_obs<CELLS>(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells);
     __syncwarp();
     store_env(w, p, rec, dirty);
 }
@@ -1061,7 +1155,7 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
     int id = map_ids ? map_ids[env] : env % p.n_maps;
     id = ((id % p.n_maps) + p.n_maps) % p.n_maps;
     reset_env(w, p, id, true);
-    if (obs) write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+    if (obs) write_obs<0>(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
     __syncwarp();
     store_env(w, p, rec, true);
 }
@@ -1074,7 +1168,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const Ste
     Ctx w;
     ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     load_env(w, p, p.records + (size_t)env * p.record_bytes);
-    write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+    write_obs<0>(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
 }
 
 // deterministic reduction of the per-env statistics: one block, fixed order
