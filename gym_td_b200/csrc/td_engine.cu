@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -16,6 +17,7 @@ struct td_handle {
     int device, kind, L, cells, cells_pad, n_envs;
     int n_maps, map_stride, difficulty;
     int record_bytes, map_bytes, smem_per_warp, scratch_off;
+    int off_static, off_towers, off_enemies;
     uint8_t *records;
     uint8_t *maps;
     uint32_t *mt;
@@ -176,6 +178,9 @@ static void fill_params(const td_handle *h, StepParams &p)
     p.map_bytes = h->map_bytes;
     p.smem_per_warp = h->smem_per_warp;
     p.scratch_off = h->scratch_off;
+    p.off_static = h->off_static;
+    p.off_towers = h->off_towers;
+    p.off_enemies = h->off_enemies;
     p.difficulty = h->difficulty;
     p.opponent_seeded = h->opponent_seeded ? 1 : 0;
 }
@@ -234,11 +239,14 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->device = device; h->kind = env_kind; h->L = map_size; h->cells = map_size * map_size;
     h->cells_pad = round16(h->cells); h->n_envs = n_envs;
     h->n_maps = 0; h->map_stride = n_envs; h->difficulty = 1;
-    h->record_bytes = kOffMap6 + h->cells_pad;
     h->map_bytes = kMapHdrBytes + 2 * h->cells_pad;
-    h->scratch_off = h->record_bytes + h->map_bytes;
+    h->off_static = kOffMap6 + h->cells_pad;
+    h->off_towers = h->off_static + h->map_bytes;
+    h->off_enemies = h->off_towers + TD_CAP_TOWERS * kTowerBytes;
+    h->record_bytes = h->off_enemies + TD_CAP_ENEMIES * kEnemyBytes;
+    h->scratch_off = h->record_bytes;
     int scratch = std::max(768, std::max(h->cells_pad, round16(2 * std::min(h->cells, 6 * map_size))));
-    h->smem_per_warp = h->scratch_off + scratch;
+    h->smem_per_warp = h->record_bytes + scratch;
     h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
     h->opponent_seeded = false; h->steps = 0;
     td_config def;
@@ -251,7 +259,10 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     if (smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
     if ((e = for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, smem); })) != cudaSuccess ||
         (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
-        (e = allow_smem(td_observe_kernel, smem)) != cudaSuccess) {
+        (e = allow_smem(td_observe_kernel<0>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_observe_kernel<100>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_observe_kernel<400>, smem)) != cudaSuccess ||
+        (e = allow_smem(td_observe_kernel<900>, smem)) != cudaSuccess) {
         h->err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e);
         return bail(TD_E_CUDA);
     }
@@ -297,8 +308,8 @@ extern "C" int td_get_layout(const td_handle *h, td_layout *out)
     if (!h || !out) return TD_E_INVALID;
     out->record_bytes = h->record_bytes;
     out->off_header = 0;
-    out->off_towers = kOffTowers;
-    out->off_enemies = kOffEnemies;
+    out->off_towers = h->off_towers;
+    out->off_enemies = h->off_enemies;
     out->off_map6 = kOffMap6;
     out->tower_stride = kTowerBytes;
     out->enemy_stride = kEnemyBytes;
@@ -386,7 +397,7 @@ __global__ void td_rng_pos_kernel(uint8_t *records, int record_bytes, int first,
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     td_env_header *h = reinterpret_cast<td_env_header *>(records + (size_t)(first + i) * record_bytes);
-    if (pos) h->rng_pos = pos[i];
+    if (pos) { h->rng_pos = pos[i]; h->pad0 = 0; }   // pad0 = cached generator words: none valid any more
     if (pos_out) pos_out[i] = h->rng_pos;
 }
 
@@ -501,10 +512,11 @@ extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
     cudaStream_t s = (cudaStream_t)stream;
     const int want = step_variant(h->kind, io->multi_action != 0);
     int seen = 0;
-    for_each_step_kernel(h, [&](auto kernel) {
+    cudaError_t le = for_each_step_kernel(h, [&](auto kernel) {
         if (seen++ == want) kernel<<<grid, block, smem, s>>>(p);
         return cudaSuccess;
     });
+    if (le != cudaSuccess) return fail(h, TD_E_CUDA, std::string("td_step: ") + cudaGetErrorString(le));
     TD_CUDA(h, cudaGetLastError());
     h->steps += h->n_envs;
     return TD_OK;
@@ -518,7 +530,15 @@ extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
     TD_CUDA(h, cudaSetDevice(h->device));
     StepParams p;
     fill_params(h, p);
-    td_observe_kernel<<<grid_of(h), kWarpsPerCta * 32, smem_of(h), (cudaStream_t)stream>>>(p, obs_dev);
+    const int grid = grid_of(h), block = kWarpsPerCta * 32;
+    const size_t smem = smem_of(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (h->L) {
+    case 10: td_observe_kernel<100><<<grid, block, smem, s>>>(p, obs_dev); break;
+    case 20: td_observe_kernel<400><<<grid, block, smem, s>>>(p, obs_dev); break;
+    case 30: td_observe_kernel<900><<<grid, block, smem, s>>>(p, obs_dev); break;
+    default: td_observe_kernel<0><<<grid, block, smem, s>>>(p, obs_dev); break;
+    }
     TD_CUDA(h, cudaGetLastError());
     return TD_OK;
 }
@@ -581,10 +601,10 @@ extern "C" int td_set_state(td_handle *h, int first_env, int n, const void *blob
         if (hd->n_towers > TD_CAP_TOWERS || hd->n_enemies > TD_CAP_ENEMIES || hd->map_id < 0 ||
             (h->n_maps > 0 && hd->map_id >= h->n_maps) || hd->rng_pos < 0 || hd->rng_pos > kMtWords)
             return fail(h, TD_E_INVALID, "td_set_state: record header out of range");
-        const td_tower_rec *tw = reinterpret_cast<const td_tower_rec *>(b + (size_t)i * h->record_bytes + kOffTowers);
+        const td_tower_rec *tw = reinterpret_cast<const td_tower_rec *>(b + (size_t)i * h->record_bytes + h->off_towers);
         for (int t = 0; t < hd->n_towers; ++t)
             if (tw[t].loc >= h->cells || (tw[t].type_lv >> 2) >= TD_NLV) return fail(h, TD_E_INVALID, "td_set_state: bad tower record");
-        const td_enemy_rec *en = reinterpret_cast<const td_enemy_rec *>(b + (size_t)i * h->record_bytes + kOffEnemies);
+        const td_enemy_rec *en = reinterpret_cast<const td_enemy_rec *>(b + (size_t)i * h->record_bytes + h->off_enemies);
         for (int e = 0; e < hd->n_enemies; ++e)
             if (en[e].loc >= h->cells || (en[e].type_lv >> 2) >= TD_NLV) return fail(h, TD_E_INVALID, "td_set_state: bad enemy record");
     }

@@ -24,18 +24,40 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+// Observation store flavour (experiments): 0 = st.global.cs (streaming), 1 = plain st.global, 2 = st.global.wt
+#ifndef TD_STORE_MODE
+#define TD_STORE_MODE 1
+#endif
+#if TD_STORE_MODE == 0
+#define TD_ST(p, v) __stcs((p), (v))
+#elif TD_STORE_MODE == 1
+#define TD_ST(p, v) (*(p) = (v))
+#else
+#define TD_ST(p, v) __stwt((p), (v))
+#endif
+#ifndef TD_WARPS_PER_CTA
+#define TD_WARPS_PER_CTA 4
+#endif
+
 namespace td {
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kWarpsPerCta = TD_WARPS_PER_CTA;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr int kHdrBytes = 64;
+// Env record in HBM (mirrored byte for byte in the warp's shared-memory slice):
+//   [ td_env_header 64 | opponent word cache 64 | map6 cells_pad | static map (MapHdr 16, cells, dist) |
+//     towers 32 x 16 | enemies 64 x 24 ]
+// Everything a step normally needs sits in two contiguous prefixes, fetched in ONE round trip: the first
+// runs from the header to tower kSpecTowers, the second covers enemies [0, kSpecEnemies).
+constexpr int kHdrBytes = 128;            // td_env_header + kRngCache cached generator words
+constexpr int kRngCache = 16;
+constexpr int kOffRngCache = 64;
 constexpr int kTowerBytes = 16;
 constexpr int kEnemyBytes = 24;
-constexpr int kOffTowers = kHdrBytes;
-constexpr int kOffEnemies = kOffTowers + TD_CAP_TOWERS * kTowerBytes;     // 576
-constexpr int kOffMap6 = kOffEnemies + TD_CAP_ENEMIES * kEnemyBytes;      // 2112
+constexpr int kOffMap6 = kHdrBytes;
 constexpr int kMapHdrBytes = 16;
 constexpr int kMtWords = 624;
+constexpr int kSpecTowers = 16;           // speculatively staged list prefixes
+constexpr int kSpecEnemies = 16;
 
 // Derived constant tables (uploaded by td_set_config).
 struct DevConfig {
@@ -76,6 +98,7 @@ struct StepParams {
     EnvStats *stats;           // [n]
     int n_envs, n_maps, map_stride;
     int L, cells, cells_pad, record_bytes, map_bytes, smem_per_warp, scratch_off;
+    int off_static, off_towers, off_enemies;
     int difficulty;
     int opponent_seeded;
     td_step_io io;
@@ -101,6 +124,9 @@ struct Ctx {
     uint32_t *mt;
     uint32_t win;
     int mt_pos, win_k, win_n;
+    const uint32_t *rng_cache;  // kRngCache raw words starting at the header's rng_pos
+    int ck, cn;                 // consumed / valid cached words
+    bool static_dirty;          // the record's static map was replaced (reset)
 };
 
 __device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16, int lane)
@@ -125,17 +151,17 @@ __device__ __forceinline__ void async_wait_all()
     __syncwarp();
 }
 
-__device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, const StepParams &p)
+__device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, uint8_t *scratch, const StepParams &p)
 {
     w.hdr = reinterpret_cast<td_env_header *>(slice);
-    w.tw = reinterpret_cast<td_tower_rec *>(slice + kOffTowers);
-    w.en = reinterpret_cast<td_enemy_rec *>(slice + kOffEnemies);
+    w.tw = reinterpret_cast<td_tower_rec *>(slice + p.off_towers);
+    w.en = reinterpret_cast<td_enemy_rec *>(slice + p.off_enemies);
     w.map6 = slice + kOffMap6;
-    uint8_t *m = slice + p.record_bytes;
+    uint8_t *m = slice + p.off_static;
     w.mh = reinterpret_cast<MapHdr *>(m);
     w.cells = m + kMapHdrBytes;
     w.dist = w.cells + p.cells_pad;
-    w.scratch = slice + p.scratch_off;
+    w.scratch = scratch;
     w.lane = threadIdx.x & 31;
     w.L = p.L;
     w.ncells = p.cells;
@@ -143,11 +169,15 @@ __device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, const StepParam
     w.ecap = TD_CAP_ENEMIES;
     w.mt = nullptr;
     w.win = 0; w.mt_pos = 0; w.win_k = 0; w.win_n = 0;
+    w.rng_cache = reinterpret_cast<const uint32_t *>(slice + kOffRngCache);
+    w.ck = 0; w.cn = 0;
+    w.static_dirty = false;
 }
 
 __device__ __forceinline__ void load_static_map(Ctx &w, const StepParams &p, int map_id)
 {
     async_copy16(w.mh, p.maps + (size_t)map_id * p.map_bytes, p.map_bytes >> 4, w.lane);
+    w.static_dirty = true;
 }
 
 __device__ __forceinline__ void pull_header(Ctx &w)
@@ -164,6 +194,8 @@ __device__ __forceinline__ void pull_header(Ctx &w)
     w.flags = h->flags;
     w.fail = TD_FC_SUCCESS;
     w.mt_pos = h->rng_pos;
+    w.ck = 0;
+    w.cn = h->pad0;             // number of valid cached generator words
 }
 
 __device__ __forceinline__ void push_header(Ctx &w)
@@ -180,6 +212,7 @@ __device__ __forceinline__ void push_header(Ctx &w)
         h->attacker_cd = (int16_t)w.atk_cd;
         h->flags = (uint8_t)w.flags;
         h->rng_pos = w.mt_pos;
+        h->pad0 = (uint8_t)w.cn;
     }
 }
 
@@ -229,6 +262,12 @@ __device__ __forceinline__ void mt_fill_window(Ctx &w)
 
 __device__ __forceinline__ uint32_t mt_next(Ctx &w)
 {
+    if (w.ck < w.cn) {                                   // words staged with the record: no extra round trip
+        uint32_t r = mt_temper(w.rng_cache[w.ck]);
+        ++w.ck;
+        ++w.mt_pos;
+        return r;
+    }
     if (w.win_k == w.win_n) {
         if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane); w.mt_pos = 0; }
         mt_fill_window(w);
@@ -239,31 +278,47 @@ __device__ __forceinline__ uint32_t mt_next(Ctx &w)
     return r;
 }
 
-// Stage one env: header + map6 first (independent), then the live prefixes and the static map.
-__device__ __forceinline__ void load_env(Ctx &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base = nullptr)
+// Stage one env in one round trip: [header .. tower kSpecTowers) and enemies [0, kSpecEnemies) are fetched
+// speculatively; only envs with longer lists pay a second trip for the rest.
+__device__ __forceinline__ void issue_env_load(uint8_t *slice, const StepParams &p, const uint8_t *rec, int lane)
 {
-    async_copy16(w.hdr, rec, kHdrBytes >> 4, w.lane);
-    async_copy16(w.map6, rec + kOffMap6, p.cells_pad >> 4, w.lane);
-    async_wait_all();
-    pull_header(w);
-    async_copy16(w.tw, rec + kOffTowers, w.nt, w.lane);                       // 16 B per tower
-    async_copy16(w.en, rec + kOffEnemies, (w.ne * 3 + 1) >> 1, w.lane);        // 24 B per enemy
-    load_static_map(w, p, w.hdr->map_id);
-    if (mt_base) {                                                            // scripted-opponent words ride along
-        w.mt = mt_base;
-        mt_fill_window(w);
-    }
-    async_wait_all();
+    async_copy16(slice, rec, (p.off_towers + kSpecTowers * kTowerBytes) >> 4, lane);
+    async_copy16(slice + p.off_enemies, rec + p.off_enemies, (kSpecEnemies * kEnemyBytes) >> 4, lane);
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
+// The speculative part has landed (caller waited): read the header, fetch the rare remainder.
+__device__ __forceinline__ void finish_env_load(Ctx &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base)
+{
+    pull_header(w);
+    w.mt = mt_base;
+    if (w.nt > kSpecTowers || w.ne > kSpecEnemies) {
+        if (w.nt > kSpecTowers)
+            async_copy16(w.tw + kSpecTowers, rec + p.off_towers + kSpecTowers * kTowerBytes, w.nt - kSpecTowers, w.lane);
+        if (w.ne > kSpecEnemies)
+            async_copy16(w.en + kSpecEnemies, rec + p.off_enemies + kSpecEnemies * kEnemyBytes,
+                         ((w.ne - kSpecEnemies) * 3 + 1) >> 1, w.lane);
+        async_wait_all();
+    }
+}
+
+__device__ __forceinline__ void load_env(Ctx &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base = nullptr)
+{
+    issue_env_load(reinterpret_cast<uint8_t *>(w.hdr), p, rec, w.lane);
+    async_wait_all();
+    finish_env_load(w, p, rec, mt_base);
+}
+
+// Write back the header block (incl. the word cache), the changed maps and the live list prefixes.
 __device__ __forceinline__ void store_env(Ctx &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
 {
     push_header(w);
     __syncwarp();
-    if (w.lane < 4) reinterpret_cast<int4 *>(rec)[w.lane] = reinterpret_cast<const int4 *>(w.hdr)[w.lane];
-    warp_copy16(rec + kOffTowers, w.tw, w.nt, w.lane);
-    warp_copy16(rec + kOffEnemies, w.en, (w.ne * 3 + 1) >> 1, w.lane);
-    if (map6_dirty) warp_copy16(rec + kOffMap6, w.map6, p.cells_pad >> 4, w.lane);
+    const uint8_t *slice = reinterpret_cast<const uint8_t *>(w.hdr);
+    const int head = w.static_dirty ? p.off_towers : (map6_dirty ? p.off_static : kHdrBytes);
+    warp_copy16(rec, slice, head >> 4, w.lane);
+    warp_copy16(rec + p.off_towers, w.tw, w.nt, w.lane);
+    warp_copy16(rec + p.off_enemies, w.en, (w.ne * 3 + 1) >> 1, w.lane);
 }
 
 // TDGymBasic.reset (:37-55) + TDBoard.__init__ (:63-79): fresh episode on map `map_id`.
@@ -836,76 +891,93 @@ __device__ __forceinline__ void fill_planes(float *o, int first_plane, int n_pla
     float4 *p = reinterpret_cast<float4 *>(o + (size_t)first_plane * cells);
     const int n4 = (n_planes * cells) >> 2;
     const float4 x = make_float4(v, v, v, v);
-    for (int q = lane; q < n4; q += 32) __stcs(p + q, x);
+    for (int q = lane; q < n4; q += 32) TD_ST(p + q, x);
 }
 
 __device__ __forceinline__ void fill_planes_scalar(float *o, int first_plane, int n_planes, int cells, float v, int lane)
 {
     float *p = o + (size_t)first_plane * cells;
-    for (int q = lane; q < n_planes * cells; q += 32) __stcs(p + q, v);
+    for (int q = lane; q < n_planes * cells; q += 32) TD_ST(p + q, v);
 }
 
-// CELLS > 0: compile-time board size -> the observation is streamed as one flat run of float4 (every
-// lane busy, plane index by constant division, broadcast values from a 45-entry shared table).
+// N4 consecutive float4 of one value, fully unrolled: one STG.128 with an immediate offset per 512 bytes.
+template <int N4>
+__device__ __forceinline__ void store_run(float4 *p, float v, int lane)
+{
+    const float4 x = make_float4(v, v, v, v);
+    constexpr int kFullIters = N4 / 32, kRem = N4 % 32;
+    p += lane;
+#pragma unroll
+    for (int k = 0; k < kFullIters; ++k) TD_ST(p + 32 * k, x);
+    if (kRem != 0 && lane < kRem) TD_ST(p + 32 * kFullIters, x);
+}
+
+// CELLS > 0: compile-time board size (runs of equal planes are unrolled stores with immediate offsets).
 // CELLS == 0: run-time board size, plane by plane (also handles L*L not divisible by 4).
 template <int CELLS>
 __device__ __forceinline__ void write_obs(Ctx &w, float *o)
 {
     const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells;
     const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-    const bool has_base = cc.base_LP >= 0;
-    const float v5 = has_base ? (float)((double)w.base_LP / (double)cc.base_LP) : 1.f;
-    const float v11 = (float)(w.cost_def / cc.max_cost);
-    const float v12 = (float)(w.cost_atk / cc.max_cost);
-    const float v13 = (float)((double)w.steps / (double)cc.max_steps);
     const float maxd = (float)w.mh->maxd_p1;
-    float vb[TD_NTYPES], vs[TD_NTYPES];
-#pragma unroll
-    for (int t = 0; t < TD_NTYPES; ++t) {
-        vb[t] = w.cost_def >= cc.tower_cost[t][0] ? 1.f : 0.f;
-        vs[t] = (float)(w.cost_def / cc.enemy_cost[t][0] / 8.0);
-    }
-    if (CELLS > 0 && vec) {
-        constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
-        constexpr int N4 = TD_NCHANNELS * C4;
-        float *pv = reinterpret_cast<float *>(w.scratch) + 64;     // [48] plane values, behind ratio[64]
+    // The 12 broadcast values (f64 quotients rounded once to f32, TDBoard.py:115-125,134-142), one per lane:
+    // lane 0 -> plane 5, 1 -> 11, 2 -> 12, 3 -> 13, 4..7 -> 41..44 (cost_def / enemy_cost / 8), 8..11 -> 21..24.
+    float *pv = reinterpret_cast<float *>(w.scratch) + 64;         // [48], behind ratio[64]
+    {
+        double num = 0.0, den = 1.0;
+        int plane = 47;
+        if (lane == 0) { num = (double)w.base_LP; den = (double)cc.base_LP; plane = 5; }
+        else if (lane == 1) { num = w.cost_def; den = cc.max_cost; plane = 11; }
+        else if (lane == 2) { num = w.cost_atk; den = cc.max_cost; plane = 12; }
+        else if (lane == 3) { num = (double)w.steps; den = (double)cc.max_steps; plane = 13; }
+        else if (lane < 8) { num = w.cost_def; den = cc.enemy_cost[lane - 4][0]; plane = 41 + lane - 4; }
+        else if (lane < 12) { plane = 21 + lane - 8; }
+        double qv = num / den;
+        if (lane >= 4 && lane < 8) qv *= 0.125;                    // "/ max_cluster_length": exact power of two
+        float val = (float)qv;
+        if (lane == 0 && cc.base_LP < 0) val = 1.f;
+        if (lane >= 8 && lane < 12) val = w.cost_def >= cc.tower_cost[lane - 8][0] ? 1.f : 0.f;
         __syncwarp();
         pv[lane] = 0.f;
         if (lane < 16) pv[32 + lane] = 0.f;
         __syncwarp();
-        if (lane == 0) {
-            pv[5] = v5; pv[11] = v11; pv[12] = v12; pv[13] = v13;
-#pragma unroll
-            for (int t = 0; t < TD_NTYPES; ++t) { pv[21 + t] = vb[t]; pv[41 + t] = vs[t]; }
-        }
+        if (lane < 12) pv[plane] = val;
         __syncwarp();
+    }
+    if (CELLS > 0 && vec) {
+        constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
+        constexpr int kIters = (C4 + 31) / 32;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells);
         const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist);
         const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6);
-#pragma unroll 4
-        for (int q = lane; q < N4; q += 32) {
-            const int pl = q / C4, i = q - pl * C4;
-            float4 v;
-            if ((0x420fu >> pl) & 1u) {                            // per-cell planes 0-3, 9, 14
-                if (pl < 4) {
-                    uchar4 c = cb[i];
-                    v = make_float4((float)((c.x >> pl) & 1), (float)((c.y >> pl) & 1),
-                                    (float)((c.z >> pl) & 1), (float)((c.w >> pl) & 1));
-                } else if (pl == 9) {
-                    uchar4 d = db[i];
-                    v = make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
-                                    __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd));
-                } else {
-                    uchar4 m = mb[i];
-                    v = make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f, m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f);
-                }
-            } else {
-                const float x = pv[pl];
-                v = make_float4(x, x, x, x);
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            const int q = lane + 32 * it;
+            if (q < C4) {
+                const uchar4 c = cb[q], d = db[q], m = mb[q];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    TD_ST(o4 + k * C4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
+                                                        (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
+                TD_ST(o4 + 9 * C4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
+                                                    __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
+                TD_ST(o4 + 14 * C4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
+                                                     m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
             }
-            __stcs(o4 + q, v);
         }
+        store_run<C4>(o4 + 4 * C4, 0.f, lane);
+        store_run<C4>(o4 + 5 * C4, pv[5], lane);
+        store_run<3 * C4>(o4 + 6 * C4, 0.f, lane);
+        store_run<C4>(o4 + 10 * C4, 0.f, lane);
+#pragma unroll
+        for (int k = 11; k < 14; ++k) store_run<C4>(o4 + k * C4, pv[k], lane);
+        store_run<6 * C4>(o4 + 15 * C4, 0.f, lane);
+#pragma unroll
+        for (int k = 21; k < 25; ++k) store_run<C4>(o4 + k * C4, pv[k], lane);
+        store_run<16 * C4>(o4 + 25 * C4, 0.f, lane);
+#pragma unroll
+        for (int k = 41; k < 45; ++k) store_run<C4>(o4 + k * C4, pv[k], lane);
     } else if (vec) {
         const int c4 = cells >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(o);
@@ -916,51 +988,38 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
             uchar4 c = cb[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                __stcs(o4 + k * c4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
+                TD_ST(o4 + k * c4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
                                                     (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
         }
         fill_planes(o, 4, 1, cells, 0.f, lane);
-        fill_planes(o, 5, 1, cells, v5, lane);
+        fill_planes(o, 5, 1, cells, pv[5], lane);
         fill_planes(o, 6, 3, cells, 0.f, lane);
         for (int q = lane; q < c4; q += 32) {
             uchar4 d = db[q];
-            __stcs(o4 + 9 * c4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
+            TD_ST(o4 + 9 * c4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
                                                 __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
         }
         fill_planes(o, 10, 1, cells, 0.f, lane);
-        fill_planes(o, 11, 1, cells, v11, lane);
-        fill_planes(o, 12, 1, cells, v12, lane);
-        fill_planes(o, 13, 1, cells, v13, lane);
+        for (int k = 11; k < 14; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
         for (int q = lane; q < c4; q += 32) {
             uchar4 m = mb[q];
-            __stcs(o4 + 14 * c4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
+            TD_ST(o4 + 14 * c4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
                                                  m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
         }
         fill_planes(o, 15, 6, cells, 0.f, lane);
-#pragma unroll
-        for (int t = 0; t < TD_NTYPES; ++t) fill_planes(o, 21 + t, 1, cells, vb[t], lane);
+        for (int k = 21; k < 25; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
         fill_planes(o, 25, 16, cells, 0.f, lane);
-#pragma unroll
-        for (int t = 0; t < TD_NTYPES; ++t) fill_planes(o, 41 + t, 1, cells, vs[t], lane);
+        for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
     } else {
         for (int q = lane; q < cells; q += 32) {
             uint8_t c = w.cells[q];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) __stcs(o + (size_t)k * cells + q, (float)((c >> k) & 1));
-            __stcs(o + (size_t)9 * cells + q, __fdiv_rn((float)w.dist[q], maxd));
-            __stcs(o + (size_t)14 * cells + q, w.map6[q] == 0 ? 1.f : 0.f);
+            for (int k = 0; k < 4; ++k) TD_ST(o + (size_t)k * cells + q, (float)((c >> k) & 1));
+            TD_ST(o + (size_t)9 * cells + q, __fdiv_rn((float)w.dist[q], maxd));
+            TD_ST(o + (size_t)14 * cells + q, w.map6[q] == 0 ? 1.f : 0.f);
         }
-        fill_planes_scalar(o, 4, 1, cells, 0.f, lane);
-        fill_planes_scalar(o, 5, 1, cells, v5, lane);
-        fill_planes_scalar(o, 6, 3, cells, 0.f, lane);
-        fill_planes_scalar(o, 10, 1, cells, 0.f, lane);
-        fill_planes_scalar(o, 11, 1, cells, v11, lane);
-        fill_planes_scalar(o, 12, 1, cells, v12, lane);
-        fill_planes_scalar(o, 13, 1, cells, v13, lane);
-        fill_planes_scalar(o, 15, 6, cells, 0.f, lane);
-        for (int t = 0; t < TD_NTYPES; ++t) fill_planes_scalar(o, 21 + t, 1, cells, vb[t], lane);
-        fill_planes_scalar(o, 25, 16, cells, 0.f, lane);
-        for (int t = 0; t < TD_NTYPES; ++t) fill_planes_scalar(o, 41 + t, 1, cells, vs[t], lane);
+        for (int k = 4; k < TD_NCHANNELS; ++k)
+            if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], lane);
     }
 
     // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
@@ -1007,24 +1066,34 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
 extern __shared__ __align__(16) uint8_t td_smem[];
 
 #ifndef TD_MIN_BLOCKS
-#define TD_MIN_BLOCKS 8
+#define TD_MIN_BLOCKS 6
 #endif
 
 template <int KIND, bool MULTI, int CELLS, int NCHUNK>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const StepParams p)
 {
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
-    Ctx w;
-    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
+    uint8_t *const slice = td_smem + (size_t)warp * p.smem_per_warp;     // [record | scratch]
     uint8_t *rec = p.records + (size_t)env * p.record_bytes;
     const td_step_io &io = p.io;
     const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
                                  !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
+    // the record and the inputs are requested together: one round trip
+    issue_env_load(slice, p, rec, lane);
+    long long in_def = 0, atk_mine = TD_NTYPES;
+    int in_opp = 0xff;
+    if (KIND != TD_KIND_ATK && !MULTI) in_def = io.def_action_dev[env];
+    if (KIND != TD_KIND_DEF && lane < TD_ROADS * TD_CLUSTER)
+        atk_mine = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane];
+    if (KIND == TD_KIND_DEF && io.opponent_dev != nullptr) in_opp = io.opponent_dev[env];
+    Ctx w;
+    ctx_bind(w, slice, slice + p.record_bytes, p);
     w.ecap = 32 * NCHUNK;
-    load_env(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
-    const int lane = w.lane;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    finish_env_load(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
     bool dirty = false;
 
     // cooldowns (TDDefense.py:38-39)
@@ -1035,7 +1104,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     int fail_def = 0;
     bool def_ok = false;
     int fail_atk[TD_ROADS] = {0, 0, 0}, n_fail_atk = 0;
-    long long atk_mine = TD_NTYPES;
 
     auto defender = [&]() {
         if (MULTI) {
@@ -1043,12 +1111,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
                          io.real_def_dev ? reinterpret_cast<long long *>(io.real_def_dev) + (size_t)env * 6 * w.ncells : nullptr,
                          dirty);
         } else {
-            long long a = io.def_action_dev[env];
-            def_ok = decode_discrete(w, a, real_def, fail_def, dirty);
+            def_ok = decode_discrete(w, in_def, real_def, fail_def, dirty);
         }
     };
     auto attacker = [&]() {
-        if (lane < TD_ROADS * TD_CLUSTER) atk_mine = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane];
         if (w.atk_cd == 0) {
             const int nr = w.mh->num_roads;
             for (int i = 0; i < nr; ++i) {
@@ -1069,7 +1135,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     if (KIND == TD_KIND_DEF) {
         defender();
         if (io.opponent_dev != nullptr) {
-            int o = io.opponent_dev[env];
+            const int o = in_opp;
             if (o != 0xff && w.atk_cd == 0) {
                 summon_uniform(w, o & 3, min((o >> 4) & 3, w.mh->num_roads - 1));
                 w.atk_cd = cc.atk_interval;
@@ -1133,8 +1199,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         reset_env(w, p, next, true);
         dirty = true;
     }
+    // Generator words for the next step: requested now, parked in the record after the observation went out.
+    uint32_t next_word = 0;
+    if (w.mt != nullptr) {
+        w.ck = 0;
+        w.cn = min(kRngCache, max(kMtWords - w.mt_pos, 0));
+        if (lane < w.cn) asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word) : "l"(w.mt + w.mt_pos + lane) : "memory");
+    }
     if (io.obs_dev) write_obs<CELLS>(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells);
     __syncwarp();
+    if (w.mt != nullptr && lane < kRngCache) const_cast<uint32_t *>(w.rng_cache)[lane] = next_word;
     store_env(w, p, rec, dirty);
 }
 
@@ -1147,9 +1221,9 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
     if (env >= p.n_envs) return;
     if (mask && !mask[env]) return;
     Ctx w;
-    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, td_smem + (size_t)warp * p.smem_per_warp + p.record_bytes, p);
     uint8_t *rec = p.records + (size_t)env * p.record_bytes;
-    if (w.lane < 4) reinterpret_cast<int4 *>(w.hdr)[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
+    if (w.lane < (kHdrBytes >> 4)) reinterpret_cast<int4 *>(w.hdr)[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
     __syncwarp();
     pull_header(w);
     int id = map_ids ? map_ids[env] : env % p.n_maps;
@@ -1160,15 +1234,16 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
     store_env(w, p, rec, true);
 }
 
+template <int CELLS>
 __global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const StepParams p, float *obs)
 {
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
     Ctx w;
-    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, td_smem + (size_t)warp * p.smem_per_warp + p.record_bytes, p);
     load_env(w, p, p.records + (size_t)env * p.record_bytes);
-    write_obs<0>(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+    write_obs<CELLS>(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
 }
 
 // deterministic reduction of the per-env statistics: one block, fixed order
