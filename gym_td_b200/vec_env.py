@@ -181,14 +181,8 @@ class TDVecEnv(object):
 
     def allreduce_stats(self):
         """Episode statistics summed over all ranks (NCCL all_reduce when torch.distributed is up)."""
-        s = self.stats()
-        keys = ["return_sum", "episodes", "length_sum", "wins", "kills", "leaks", "steps"]
-        v = torch.tensor([float(s[k]) for k in keys], dtype=torch.float64, device=self.device)
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(v, op=dist.ReduceOp.SUM)
-        out = {k: (float(x) if k == "return_sum" else int(x)) for k, x in zip(keys, v.tolist())}
-        return out
+        from . import dist
+        return dist.reduce_stats(self.stats(), self.device)
 
     def close(self):
         self.engine.close()

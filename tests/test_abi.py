@@ -1,0 +1,70 @@
+"""The C-ABI shared library: loads, exports every symbol include/td_b200.h declares, validates arguments
+and fails loudly without a GPU (no compute call is made here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from gym_td_b200 import engine as E
+from gym_td_b200 import params
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "td_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(td_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_symbols_are_exported():
+    lib = E.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "libtd_b200.so lacks %s" % n
+    assert sorted(E.EXPORTS) == names
+    assert lib.td_abi_version() == 1
+
+
+def test_struct_sizes_match_header():
+    assert C.sizeof(E.TdConfig) == 8 * 8 * 7 + 4 * 8 * 2 + 8 * 12 + 4 * 8
+    assert C.sizeof(E.TdMap) == 4 * 8 + 2 * 64 * 64
+    assert C.sizeof(E.TdStats) == 64
+    assert E.HEADER_DTYPE.itemsize == 64
+
+
+def test_default_config_equals_reference_values():
+    c = E.config_struct(params.Config())
+    assert [list(r) for r in c.enemy_LP] == [[820, 1700], [2050, 3000], [6000, 8000], [8000, 12000]]
+    assert [list(r) for r in c.tower_attack_interval][3] == [4.75, 4.75]
+    assert (c.base_LP, c.max_cost, c.tower_distance, c.max_episode_steps, c.frozen_time) == (5, 100.0, 2, 1200, 2)
+    cfg = params.Config()
+    cfg.base_LP = None
+    assert E.config_struct(cfg).base_LP == -1
+    cfg.max_tower_lv = 2
+    with pytest.raises(ValueError):
+        E.config_struct(cfg)
+
+
+def test_create_validates_and_reports():
+    lib = E.lib()
+    h = C.c_void_p()
+    c = E.config_struct()
+    assert lib.td_create(C.byref(c), 7, 10, 4, 0, C.byref(h)) == -1
+    assert b"kind" in lib.td_last_error(None)
+    assert lib.td_create(C.byref(c), 0, 3, 4, 0, C.byref(h)) == -1
+    assert lib.td_create(C.byref(c), 0, 10, 0, 0, C.byref(h)) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(E.TdError) as ei:
+        E.Engine("def", 10, 4)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+    import gym_td_b200
+    with pytest.raises(E.TdError):
+        gym_td_b200.make("TD-def-small-v0", seed=1)

@@ -1,0 +1,282 @@
+"""GPU tests of the host layer: drop-in façade envs, batched env semantics, statistics, state access,
+capacity flagging and full-size properties (BASELINE.json sizes)."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+from tests import golden_util as GU
+from tests import parity_util as PU
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("kind,L", [("def", 10), ("2p", 10), ("atk", 10), ("def", 20), ("atk", 30)])
+def test_facade_reproduces_survey_known_answers(kind, L):
+    """The script that produced SURVEY.md 8(c)'s digests from the reference, run on this package instead."""
+    import gym_td_b200 as G
+    kats = {(k["kind"], k["L"]): k for k in json.load(open(os.path.join(GU.GOLDEN, "survey_kats.json")))}
+    k = kats[(kind, L)]
+    rs = np.random.RandomState(0)
+    if kind == "def":
+        env = G.TDDefense(L, seed=1024, random_agent=False)
+    elif kind == "2p":
+        env = G.TDMulti(L, seed=1024, random_agent=False)
+    else:
+        random.seed(1024)
+        env = G.TDAttack(L, seed=1024, random_agent=True)
+    assert env.observation_space.shape == (45, L, L) and env.num_roads in (1, 2, 3)
+    h = hashlib.sha256()
+    h.update(env._board.get_states().tobytes())
+    ret, n = 0.0, 0
+    while True:
+        if kind == "def":
+            a = int(rs.randint(6 * L * L + 1))
+        elif kind == "2p":
+            atk = rs.randint(0, 5, size=(3, 8))
+            a = {"Attacker": atk, "Defender": int(rs.randint(6 * L * L + 1))}
+        else:
+            a = rs.randint(0, 5, size=(3, 8))
+        o, r, d, info = env.step(a)
+        assert o.dtype == np.float32 and isinstance(r, float) and isinstance(d, bool)
+        assert set(info) == {"RealAction", "Win", "AllowNextMove", "FailCode"}
+        h.update(o.tobytes())
+        h.update(np.float64(r).tobytes())
+        ret += r
+        n += 1
+        if d:
+            break
+    assert (n, repr(ret), h.hexdigest()[:16]) == (k["steps"], k["ret"], k["sha"])
+    assert info["Win"] is not None
+    env.close()
+
+
+def test_facade_against_live_reference():
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference not present on this box")
+    import gym_td_b200 as G
+    from oracle import ref_harness as RH
+    ref_loader.load()
+    np.seterr(all="ignore")
+    for kind, L, seed in (("def", 10, 1024), ("atk", 10, 1024), ("2p", 20, 1024)):
+        ref = RH.make_env(kind, L, seed)
+        assert ref is not None
+        random.seed(seed)
+        st0 = random.getstate()
+        mine = G.make("TD-%s-%s-v0" % (kind, {10: "small", 20: "middle"}[L]), seed=seed)
+        assert np.array_equal(ref._board.get_states(), mine._board.get_states())
+        assert mine.num_roads == ref.num_roads
+        rs = np.random.RandomState(3)
+        st_ref = st_mine = st0
+        for t in range(250):
+            if kind == "atk":
+                a = rs.randint(0, 5, size=(3, 8))
+            elif kind == "def":
+                a = RH.smart_defender_action(ref._board, rs)
+            else:
+                a = {"Attacker": rs.randint(0, 5, size=(3, 8)), "Defender": RH.smart_defender_action(ref._board, rs)}
+            random.setstate(st_ref)
+            o1, r1, d1, i1 = ref.step(a)
+            st_ref = random.getstate()
+            random.setstate(st_mine)
+            o2, r2, d2, i2 = mine.step(a)
+            st_mine = random.getstate()
+            assert st_ref == st_mine                         # the global `random` stream advanced identically
+            assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32)) and repr(r1) == repr(r2) and d1 == d2
+            assert type(i1["RealAction"]) == type(i2["RealAction"]) or kind != "2p"
+            assert repr(i1["Win"]) == repr(i2["Win"]) and i1["AllowNextMove"] == i2["AllowNextMove"]
+            if isinstance(i1["RealAction"], dict):
+                assert np.array_equal(i1["RealAction"]["Attacker"], i2["RealAction"]["Attacker"])
+                assert i1["RealAction"]["Defender"] == i2["RealAction"]["Defender"]
+            else:
+                assert np.array_equal(np.asarray(i1["RealAction"]), np.asarray(i2["RealAction"]))
+            assert json.dumps(i1["FailCode"], default=int) == json.dumps(i2["FailCode"], default=int)
+            b1, b2 = ref._board, mine._board
+            assert repr(float(b1.cost_def)) == repr(b2.cost_def) and len(b1.towers) == len(b2.towers)
+            assert [(e.loc, int(e.type), float(e.LP)) for e in b1.enemies] == [(e.loc, e.type, e.LP) for e in b2.enemies]
+            if d1:
+                break
+        o1 = ref.reset()                                      # second draw from the same np_random stream
+        o2 = mine.reset()
+        if o1 is not None:
+            assert np.array_equal(o1, o2)
+        mine.close()
+
+
+def test_invalid_action_asserts_like_the_reference():
+    import gym_td_b200 as G
+    env = G.make("TD-def-small-v0", seed=5)
+    with pytest.raises(AssertionError):
+        env.step(601)
+    with pytest.raises(AssertionError):
+        env.step(1.5)
+    assert env.empty_action() == 600
+    env.close()
+    atk = G.make("TD-atk-small-v0", seed=5)
+    with pytest.raises(AssertionError):
+        atk.step(np.full((3, 8), 5))
+    assert atk.empty_action().shape == (3, 8)
+    atk.close()
+
+
+def test_vec_env_auto_reset_statistics_and_host_path():
+    """TDVecEnv over several episodes vs per-env oracles restarted on the next map; statistics; step_host."""
+    import torch
+    from gym_td_b200 import mapgen
+    from gym_td_b200.vec_env import TDVecEnv
+    from oracle import td_oracle as TO
+    N, L = 24, 10
+    cfg = PU.make_config(max_episode_steps=150)
+    env = TDVecEnv("def", L, N, seed=400, auto_reset=True, cfg=cfg)
+    ocfg = PU.oracle_config_from_engine(cfg)
+    maps, _, _ = mapgen.generate_batch((np.arange(N) + 400).astype(np.uint32), L)
+    oracles, map_id = [], list(range(N))
+    for i in range(N):
+        o = PU.oracle_env_from_map(maps[i], ocfg)
+        o.set_pyrand(random.Random(400 + i).getstate())
+        oracles.append(o)
+    env.reset()
+    rs = np.random.RandomState(9)
+    tot = dict(episodes=0, ret=0.0, length=0, wins=0, kills=0, leaks=0)
+    ep_ret = [0.0] * N
+    acts_pinned = torch.empty(N, dtype=torch.int64).pin_memory()
+    for step in range(400):
+        a = np.array([PU.smart_defender_action(o, rs) for o in oracles], dtype=np.int64)
+        if step % 2 == 0:
+            obs, rew, done, info = env.step(torch.from_numpy(a).cuda())
+            torch.cuda.synchronize()
+            rew_h, done_h = rew.cpu().numpy(), done.cpu().numpy()
+        else:                                                  # same step through the host-buffer ABI call
+            acts_pinned.copy_(torch.from_numpy(a))
+            h = env.step_host(acts_pinned)
+            rew_h, done_h = h["reward"].numpy().copy(), h["done"].numpy().astype(bool)
+        obs_h = env.obs.cpu().numpy()
+        for i, o in enumerate(oracles):
+            out = o.def_step(int(a[i]), 1, False)
+            assert float(rew_h[i]).hex() == float(out.reward).hex() and bool(done_h[i]) == bool(out.done), (step, i)
+            ep_ret[i] += out.reward
+            tot["kills"] += o.e.last_kills
+            tot["leaks"] += o.e.last_leaks
+            if out.done:
+                tot["episodes"] += 1
+                tot["ret"] += ep_ret[i]
+                tot["length"] += o.e.steps
+                tot["wins"] += int(out.win)
+                ep_ret[i] = 0.0
+                map_id[i] = (map_id[i] + 1) % N                # map_stride = 1
+                py = o.e.pyrand                                # the opponent stream keeps running across episodes
+                oracles[i] = o = PU.oracle_env_from_map(maps[map_id[i]], ocfg)
+                o.e.pyrand = py
+            assert np.array_equal(obs_h[i].view(np.uint32), o.get_states().view(np.uint32)), (step, i)
+    st = env.stats()
+    assert st["episodes"] == tot["episodes"] > N and st["length_sum"] == tot["length"] and st["wins"] == tot["wins"]
+    assert st["steps"] == 400 * N and st["overflow_envs"] == 0
+    assert abs(st["return_sum"] - tot["ret"]) < 1e-9 * max(1.0, abs(tot["ret"]))
+    # kills/leaks are accumulated per finished episode on the device
+    assert st["kills"] <= tot["kills"] and st["leaks"] <= tot["leaks"]
+    assert env.allreduce_stats()["episodes"] == st["episodes"]
+    env.close()
+
+
+def test_observe_and_state_round_trip():
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    env = TDVecEnv("2p", 20, 8, seed=3, auto_reset=False, scripted_opponent=False)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for _ in range(120):
+        a = {"Attacker": torch.randint(0, 5, (8, 3, 8), device="cuda", generator=g),
+             "Defender": torch.randint(0, 2401, (8,), device="cuda", generator=g)}
+        env.step(a)
+    ref_obs = env.obs.clone()
+    out = torch.zeros_like(ref_obs)
+    env.engine.observe(out, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out.view(torch.int32), ref_obs.view(torch.int32))       # kernel (f) alone == fused path
+    blob = env.engine.get_state_raw()
+    blob2 = blob.copy()
+    blob2[1] = blob[0]                                                          # clone env 0 into env 1
+    hdr = blob2[1][:64].view(np.uint8)
+    env.engine.set_state_raw(blob2)
+    env.engine.observe(out, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert torch.equal(out[1].view(torch.int32), ref_obs[0].view(torch.int32))
+    bad = blob.copy()
+    bad[0][44] = 200                                                            # n_towers > capacity
+    with pytest.raises(Exception):
+        env.engine.set_state_raw(bad)
+    env.close()
+
+
+def test_capacity_overflow_is_flagged_not_silent():
+    import torch
+    from gym_td_b200 import engine as E
+    from gym_td_b200.vec_env import TDVecEnv
+    cheap = [[1, 1]] * 4
+    cfg = PU.make_config(enemy_cost=cheap, attacker_init_cost=100, base_LP=None,
+                         enemy_speed=[[.01, .01]] * 4)
+    env = TDVecEnv("atk", 10, 4, seed=1, auto_reset=False, scripted_opponent=False, cfg=cfg)
+    env.reset()
+    a = torch.zeros((4, 3, 8), dtype=torch.int64, device="cuda")
+    for _ in range(12):
+        env.step(a)
+    with pytest.raises(E.TdError):
+        env.stats()
+    env.close()
+
+
+def test_full_size_determinism_and_replayed_subset():
+    """BASELINE.json config 2: 65,536 envs, Discrete actions; the first 256 envs replayed through the oracle;
+    size-independent properties on the whole batch (broadcast planes equal the state, determinism)."""
+    import torch
+    from gym_td_b200 import mapgen
+    from gym_td_b200.vec_env import TDVecEnv
+    N, L, K, SUB = 65536, 10, 120, 256
+    g = torch.Generator(device="cuda").manual_seed(7)
+    acts = torch.randint(0, 601, (K, N), dtype=torch.int64, device="cuda", generator=g)
+
+    def run():
+        env = TDVecEnv("def", L, N, seed=0, auto_reset=True)
+        env.reset()
+        sums, subs = [], []
+        for k in range(K):
+            obs, rew, done, info = env.step(acts[k])
+            sums.append((obs.view(torch.int32).sum(dtype=torch.int64).item(), rew.sum().item(), done.sum().item()))
+            subs.append((obs[:SUB].cpu().numpy(), rew[:SUB].cpu().numpy(), done[:SUB].cpu().numpy()))
+        blob = env.engine.get_state_raw(0, 2048)
+        hdr = np.stack([b[:64].view(E.HEADER_DTYPE)[0] for b in blob])
+        o = env.obs[:2048].cpu().numpy()
+        env.close()
+        return sums, subs, hdr, o
+
+    from gym_td_b200 import engine as E
+    s1, sub1, hdr, o = run()
+    s2, _, _, _ = run()
+    assert s1 == s2                                                    # bitwise deterministic at full size
+    # broadcast planes are pure functions of the record header
+    assert np.array_equal(o[:, 11, 0, 0], (hdr["cost_def"] / 100.0).astype(np.float32))
+    assert np.array_equal(o[:, 12, 3, 4], (hdr["cost_atk"] / 100.0).astype(np.float32))
+    assert np.array_equal(o[:, 13, 9, 9], (hdr["steps"] / 1200).astype(np.float32))
+    assert np.array_equal(o[:, 5, 2, 2], (hdr["base_LP"] / 5).astype(np.float32))
+    assert (o[:, 10] == 0).all() and (o[:, 11].min(axis=(1, 2)) == o[:, 11].max(axis=(1, 2))).all()
+    # replayed subset
+    maps, _, _ = mapgen.generate_batch(np.arange(N, dtype=np.uint32), L)
+    ocfg = PU.oracle_config_from_engine(PU.make_config())
+    acts_h = acts[:, :SUB].cpu().numpy()
+    for i in range(SUB):
+        oenv = PU.oracle_env_from_map(maps[i], ocfg)
+        oenv.set_pyrand(random.Random(i).getstate())
+        mid = i
+        for k in range(K):
+            out = oenv.def_step(int(acts_h[k, i]), 1, False)
+            assert float(sub1[k][1][i]).hex() == float(out.reward).hex() and bool(sub1[k][2][i]) == bool(out.done), (i, k)
+            if out.done:
+                py = oenv.e.pyrand
+                mid = (mid + 1) % N
+                oenv = PU.oracle_env_from_map(maps[mid], ocfg)
+                oenv.e.pyrand = py
+            assert np.array_equal(sub1[k][0][i].view(np.uint32), oenv.get_states().view(np.uint32)), (i, k)

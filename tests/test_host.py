@@ -1,0 +1,51 @@
+"""Host-side mirror of the reference interface: config API, registry, spaces, sharding."""
+import numpy as np
+import pytest
+
+import gym_td_b200 as G
+from gym_td_b200 import dist, params, spaces
+
+
+def test_param_api_matches_reference_behaviour():
+    assert G.getConfig() is params.config.__dict__               # TDParam.py:102-103 returns the live dict
+    old = params.config.max_cost
+    G.paramConfig(max_cost=77, brand_new_key=1)                  # bare setattr, unknown keys accepted (:98-100)
+    assert params.config.max_cost == 77 and params.config.brand_new_key == 1
+    G.paramConfig(max_cost=old)
+    del params.config.brand_new_key
+    hp = G.getHyperParameters()
+    assert hp == dict(max_episode_steps=1200, video_frames_per_second=50, allow_multiple_actions=False,
+                      max_cluster_length=8, max_num_of_roads=3)
+    hp["max_episode_steps"] = 5                                  # a copy (:117-118)
+    assert G.hyper_parameters.max_episode_steps == 1200
+    with pytest.raises(RuntimeError):
+        G.hyper_parameters.max_episode_steps = 3                 # :112-113
+    assert params.n_channels() == 45
+
+
+def test_registry_has_the_twelve_ids():
+    ids = sorted(G.REGISTRY)
+    assert len(ids) == 12 and "TD-def-small-v0" in ids and "TD-2p-v0" in ids
+    assert G.REGISTRY["TD-atk-middle-v0"] == ("TDAttack", {"map_size": 20})
+    assert G.REGISTRY["TD-def-v0"] == ("TDDefense", {})
+
+
+def test_spaces_contains_semantics():
+    d = spaces.Discrete(601)
+    assert d.contains(600) and d.contains(np.int64(0)) and not d.contains(601) and not d.contains(1.0)
+    b = spaces.Box(low=0, high=4, shape=(3, 8), dtype=np.int64)
+    assert b.contains(np.full((3, 8), 4)) and not b.contains(np.full((3, 8), 5)) and not b.contains(np.zeros((3, 7)))
+    assert not b.contains(np.zeros((3, 8), dtype=np.float64))
+    dd = spaces.Dict({"Attacker": b, "Defender": d})
+    assert dd.contains({"Attacker": np.zeros((3, 8), dtype=np.int64), "Defender": 3})
+    assert not dd.contains({"Attacker": np.zeros((3, 8), dtype=np.int64)})
+    assert b.sample().shape == (3, 8)
+
+
+def test_shard_ranges_partition_the_envs():
+    for n, world in ((65536, 8), (10, 3), (7, 8)):
+        r = [dist.shard_range(n, k, world) for k in range(world)]
+        assert r[0][0] == 0 and r[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+        assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
+    assert dist.env_seeds(5, 2, 5) == [7, 8, 9]
