@@ -531,7 +531,11 @@ extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
     StepParams p;
     fill_params(h, p);
     const int grid = grid_of(h), block = kWarpsPerCta * 32;
-    const size_t smem = smem_of(h);
+    size_t smem = smem_of(h);
+    if (const char *ev = getenv("TD_OBS_SMEM_KB")) {            // experiments: throttle occupancy of the store kernel
+        smem = std::max(smem, (size_t)atoi(ev) * 1024);
+        cudaFuncSetAttribute(td_observe_kernel<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
     cudaStream_t s = (cudaStream_t)stream;
     switch (h->L) {
     case 10: td_observe_kernel<100><<<grid, block, smem, s>>>(p, obs_dev); break;

@@ -107,16 +107,16 @@ struct StepParams {
 // ------------------------------------------------------------------------------------------------
 // per-warp context: pointers into the warp's shared-memory slice + uniform registers
 
+// CELLS > 0: board size known at compile time -> every pointer into the slice is base + constant.
+// CELLS == 0: layout read from the kernel parameters (constant bank).
+template <int CELLS>
 struct Ctx {
-    td_env_header *hdr;
-    td_tower_rec *tw;
-    td_enemy_rec *en;
-    uint8_t *map6;
-    MapHdr *mh;
-    uint8_t *cells;
-    uint8_t *dist;
-    uint8_t *scratch;          // >= 512 bytes (+128 byte index scratch behind it)
-    int lane, L, ncells, cells_pad, ecap;
+    static constexpr int kCells = CELLS;
+    static constexpr int kL = CELLS == 100 ? 10 : CELLS == 400 ? 20 : CELLS == 900 ? 30 : 0;
+    static constexpr int kPad = (CELLS + 15) & ~15;
+    uint8_t *slice;            // the warp's shared-memory slice: [record | scratch]
+    const StepParams *pp;
+    int lane, ecap;
     // uniform copies of hot header fields (identical in all lanes)
     double cost_def, cost_atk;
     int nt, ne, base_LP, steps, def_cd, atk_cd, fail, flags;
@@ -124,9 +124,26 @@ struct Ctx {
     uint32_t *mt;
     uint32_t win;
     int mt_pos, win_k, win_n;
-    const uint32_t *rng_cache;  // kRngCache raw words starting at the header's rng_pos
     int ck, cn;                 // consumed / valid cached words
     bool static_dirty;          // the record's static map was replaced (reset)
+
+    __device__ __forceinline__ int L() const { return CELLS ? kL : pp->L; }
+    __device__ __forceinline__ int ncells() const { return CELLS ? CELLS : pp->cells; }
+    __device__ __forceinline__ int cells_pad() const { return CELLS ? kPad : pp->cells_pad; }
+    __device__ __forceinline__ int map_bytes() const { return kMapHdrBytes + 2 * cells_pad(); }
+    __device__ __forceinline__ int off_static() const { return kOffMap6 + cells_pad(); }
+    __device__ __forceinline__ int off_towers() const { return off_static() + map_bytes(); }
+    __device__ __forceinline__ int off_enemies() const { return off_towers() + TD_CAP_TOWERS * kTowerBytes; }
+    __device__ __forceinline__ int record_bytes() const { return off_enemies() + TD_CAP_ENEMIES * kEnemyBytes; }
+    __device__ __forceinline__ td_env_header *hdr() const { return reinterpret_cast<td_env_header *>(slice); }
+    __device__ __forceinline__ const uint32_t *rng_cache() const { return reinterpret_cast<const uint32_t *>(slice + kOffRngCache); }
+    __device__ __forceinline__ uint8_t *map6() const { return slice + kOffMap6; }
+    __device__ __forceinline__ MapHdr *mh() const { return reinterpret_cast<MapHdr *>(slice + off_static()); }
+    __device__ __forceinline__ uint8_t *cells() const { return slice + off_static() + kMapHdrBytes; }
+    __device__ __forceinline__ uint8_t *dist() const { return slice + off_static() + kMapHdrBytes + cells_pad(); }
+    __device__ __forceinline__ td_tower_rec *tw() const { return reinterpret_cast<td_tower_rec *>(slice + off_towers()); }
+    __device__ __forceinline__ td_enemy_rec *en() const { return reinterpret_cast<td_enemy_rec *>(slice + off_enemies()); }
+    __device__ __forceinline__ uint8_t *scratch() const { return slice + record_bytes(); }
 };
 
 __device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16, int lane)
@@ -151,38 +168,30 @@ __device__ __forceinline__ void async_wait_all()
     __syncwarp();
 }
 
-__device__ __forceinline__ void ctx_bind(Ctx &w, uint8_t *slice, uint8_t *scratch, const StepParams &p)
+template <class W>
+__device__ __forceinline__ void ctx_bind(W &w, uint8_t *slice, const StepParams &p)
 {
-    w.hdr = reinterpret_cast<td_env_header *>(slice);
-    w.tw = reinterpret_cast<td_tower_rec *>(slice + p.off_towers);
-    w.en = reinterpret_cast<td_enemy_rec *>(slice + p.off_enemies);
-    w.map6 = slice + kOffMap6;
-    uint8_t *m = slice + p.off_static;
-    w.mh = reinterpret_cast<MapHdr *>(m);
-    w.cells = m + kMapHdrBytes;
-    w.dist = w.cells + p.cells_pad;
-    w.scratch = scratch;
+    w.slice = slice;
+    w.pp = &p;
     w.lane = threadIdx.x & 31;
-    w.L = p.L;
-    w.ncells = p.cells;
-    w.cells_pad = p.cells_pad;
     w.ecap = TD_CAP_ENEMIES;
     w.mt = nullptr;
     w.win = 0; w.mt_pos = 0; w.win_k = 0; w.win_n = 0;
-    w.rng_cache = reinterpret_cast<const uint32_t *>(slice + kOffRngCache);
     w.ck = 0; w.cn = 0;
     w.static_dirty = false;
 }
 
-__device__ __forceinline__ void load_static_map(Ctx &w, const StepParams &p, int map_id)
+template <class W>
+__device__ __forceinline__ void load_static_map(W &w, const StepParams &p, int map_id)
 {
-    async_copy16(w.mh, p.maps + (size_t)map_id * p.map_bytes, p.map_bytes >> 4, w.lane);
+    async_copy16(w.mh(), p.maps + (size_t)map_id * w.map_bytes(), w.map_bytes() >> 4, w.lane);
     w.static_dirty = true;
 }
 
-__device__ __forceinline__ void pull_header(Ctx &w)
+template <class W>
+__device__ __forceinline__ void pull_header(W &w)
 {
-    const td_env_header *h = w.hdr;
+    const td_env_header *h = w.hdr();
     w.cost_def = h->cost_def;
     w.cost_atk = h->cost_atk;
     w.nt = h->n_towers;
@@ -198,10 +207,11 @@ __device__ __forceinline__ void pull_header(Ctx &w)
     w.cn = h->pad0;             // number of valid cached generator words
 }
 
-__device__ __forceinline__ void push_header(Ctx &w)
+template <class W>
+__device__ __forceinline__ void push_header(W &w)
 {
     if (w.lane == 0) {
-        td_env_header *h = w.hdr;
+        td_env_header *h = w.hdr();
         h->cost_def = w.cost_def;
         h->cost_atk = w.cost_atk;
         h->n_towers = (uint8_t)w.nt;
@@ -252,7 +262,8 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 }
 
 // Load the next <= 32 words (untempered) into the lanes; a no-op when the state needs a twist first.
-__device__ __forceinline__ void mt_fill_window(Ctx &w)
+template <class W>
+__device__ __forceinline__ void mt_fill_window(W &w)
 {
     int n = kMtWords - w.mt_pos;
     w.win_n = n < 32 ? (n < 0 ? 0 : n) : 32;
@@ -260,10 +271,11 @@ __device__ __forceinline__ void mt_fill_window(Ctx &w)
     w.win = w.lane < w.win_n ? w.mt[w.mt_pos + w.lane] : 0u;
 }
 
-__device__ __forceinline__ uint32_t mt_next(Ctx &w)
+template <class W>
+__device__ __forceinline__ uint32_t mt_next(W &w)
 {
     if (w.ck < w.cn) {                                   // words staged with the record: no extra round trip
-        uint32_t r = mt_temper(w.rng_cache[w.ck]);
+        uint32_t r = mt_temper(w.rng_cache()[w.ck]);
         ++w.ck;
         ++w.mt_pos;
         return r;
@@ -280,58 +292,62 @@ __device__ __forceinline__ uint32_t mt_next(Ctx &w)
 
 // Stage one env in one round trip: [header .. tower kSpecTowers) and enemies [0, kSpecEnemies) are fetched
 // speculatively; only envs with longer lists pay a second trip for the rest.
-__device__ __forceinline__ void issue_env_load(uint8_t *slice, const StepParams &p, const uint8_t *rec, int lane)
+template <class W>
+__device__ __forceinline__ void issue_env_load(W &w, const uint8_t *rec)
 {
-    async_copy16(slice, rec, (p.off_towers + kSpecTowers * kTowerBytes) >> 4, lane);
-    async_copy16(slice + p.off_enemies, rec + p.off_enemies, (kSpecEnemies * kEnemyBytes) >> 4, lane);
+    async_copy16(w.slice, rec, (w.off_towers() + kSpecTowers * kTowerBytes) >> 4, w.lane);
+    async_copy16(w.en(), rec + w.off_enemies(), (kSpecEnemies * kEnemyBytes) >> 4, w.lane);
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 // The speculative part has landed (caller waited): read the header, fetch the rare remainder.
-__device__ __forceinline__ void finish_env_load(Ctx &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base)
+template <class W>
+__device__ __forceinline__ void finish_env_load(W &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base)
 {
     pull_header(w);
     w.mt = mt_base;
     if (w.nt > kSpecTowers || w.ne > kSpecEnemies) {
         if (w.nt > kSpecTowers)
-            async_copy16(w.tw + kSpecTowers, rec + p.off_towers + kSpecTowers * kTowerBytes, w.nt - kSpecTowers, w.lane);
+            async_copy16(w.tw() + kSpecTowers, rec + w.off_towers() + kSpecTowers * kTowerBytes, w.nt - kSpecTowers, w.lane);
         if (w.ne > kSpecEnemies)
-            async_copy16(w.en + kSpecEnemies, rec + p.off_enemies + kSpecEnemies * kEnemyBytes,
+            async_copy16(w.en() + kSpecEnemies, rec + w.off_enemies() + kSpecEnemies * kEnemyBytes,
                          ((w.ne - kSpecEnemies) * 3 + 1) >> 1, w.lane);
         async_wait_all();
     }
 }
 
-__device__ __forceinline__ void load_env(Ctx &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base = nullptr)
+template <class W>
+__device__ __forceinline__ void load_env(W &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base = nullptr)
 {
-    issue_env_load(reinterpret_cast<uint8_t *>(w.hdr), p, rec, w.lane);
+    issue_env_load(w, rec);
     async_wait_all();
     finish_env_load(w, p, rec, mt_base);
 }
 
 // Write back the header block (incl. the word cache), the changed maps and the live list prefixes.
-__device__ __forceinline__ void store_env(Ctx &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
+template <class W>
+__device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
 {
     push_header(w);
     __syncwarp();
-    const uint8_t *slice = reinterpret_cast<const uint8_t *>(w.hdr);
-    const int head = w.static_dirty ? p.off_towers : (map6_dirty ? p.off_static : kHdrBytes);
-    warp_copy16(rec, slice, head >> 4, w.lane);
-    warp_copy16(rec + p.off_towers, w.tw, w.nt, w.lane);
-    warp_copy16(rec + p.off_enemies, w.en, (w.ne * 3 + 1) >> 1, w.lane);
+    const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : kHdrBytes);
+    warp_copy16(rec, w.slice, head >> 4, w.lane);
+    warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane);
+    warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane);
 }
 
 // TDGymBasic.reset (:37-55) + TDBoard.__init__ (:63-79): fresh episode on map `map_id`.
-__device__ __forceinline__ void reset_env(Ctx &w, const StepParams &p, int map_id, bool reload_map)
+template <class W>
+__device__ __forceinline__ void reset_env(W &w, const StepParams &p, int map_id, bool reload_map)
 {
     if (reload_map) {
         __syncwarp();
         load_static_map(w, p, map_id);
         async_wait_all();
     }
-    for (int q = w.lane; q < (p.cells_pad >> 2); q += 32) {
-        uint32_t c4 = reinterpret_cast<const uint32_t *>(w.cells)[q];
-        reinterpret_cast<uint32_t *>(w.map6)[q] = c4 & 0x01010101u;           // map[6] = 1 on road cells
+    for (int q = w.lane; q < (w.cells_pad() >> 2); q += 32) {
+        uint32_t c4 = reinterpret_cast<const uint32_t *>(w.cells())[q];
+        reinterpret_cast<uint32_t *>(w.map6())[q] = c4 & 0x01010101u;           // map[6] = 1 on road cells
     }
     w.cost_def = cc.def_init_cost;
     w.cost_atk = cc.atk_init_cost;
@@ -343,16 +359,17 @@ __device__ __forceinline__ void reset_env(Ctx &w, const StepParams &p, int map_i
     w.atk_cd = 0;
     w.fail = TD_FC_SUCCESS;
     if (w.lane == 0) {
-        w.hdr->map_id = map_id;
-        w.hdr->ep_return = 0.0;
-        w.hdr->ep_kills = 0;
-        w.hdr->ep_leaks = 0;
+        w.hdr()->map_id = map_id;
+        w.hdr()->ep_return = 0.0;
+        w.hdr()->ep_kills = 0;
+        w.hdr()->ep_leaks = 0;
     }
     __syncwarp();
 }
 
 // random._randbelow_with_getrandbits(n), 1 <= n < 2^31
-__device__ __forceinline__ int py_randbelow(Ctx &w, int n)
+template <class W>
+__device__ __forceinline__ int py_randbelow(W &w, int n)
 {
     int shift = __clz(n);            // 32 - bit_length(n)
     uint32_t r = mt_next(w) >> shift;
@@ -360,7 +377,8 @@ __device__ __forceinline__ int py_randbelow(Ctx &w, int n)
     return (int)r;
 }
 
-__device__ __forceinline__ double py_random(Ctx &w)
+template <class W>
+__device__ __forceinline__ double py_random(W &w)
 {
     uint32_t a = mt_next(w) >> 5, b = mt_next(w) >> 6;
     return __dmul_rn(__dadd_rn(__dmul_rn((double)a, 67108864.0), (double)b), 1.0 / 9007199254740992.0);
@@ -369,27 +387,29 @@ __device__ __forceinline__ double py_random(Ctx &w)
 // ------------------------------------------------------------------------------------------------
 // (a) defender operations -- all arguments and results are warp-uniform
 
-__device__ __forceinline__ void diamond_add(Ctx &w, int loc, int delta)
+template <class W>
+__device__ __forceinline__ void diamond_add(W &w, int loc, int delta)
 {
-    const int L = w.L, D = cc.tower_distance, W = 2 * D + 1;
+    const int L = w.L(), D = cc.tower_distance, WD = 2 * D + 1;
     const int r0 = loc / L, c0 = loc - r0 * L;
-    for (int k = w.lane; k < W * W; k += 32) {
-        int i = k / W - D, j = k % W - D;
+    for (int k = w.lane; k < WD * WD; k += 32) {
+        int i = k / WD - D, j = k % WD - D;
         int r = r0 + i, c = c0 + j;
         if (abs(i) + abs(j) <= D && r >= 0 && r < L && c >= 0 && c < L)
-            w.map6[r * L + c] = (uint8_t)(w.map6[r * L + c] + delta);
+            w.map6()[r * L + c] = (uint8_t)(w.map6()[r * L + c] + delta);
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ bool tower_build(Ctx &w, int t, int loc, bool &map6_dirty)   // TDBoard.py:226-247
+template <class W>
+__device__ __forceinline__ bool tower_build(W &w, int t, int loc, bool &map6_dirty)   // TDBoard.py:226-247
 {
     const double cost = cc.tower_cost[t][0];
     if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
-    if (w.map6[loc] > 0) { w.fail = TD_FC_INVALID_POSITION; return false; }
+    if (w.map6()[loc] > 0) { w.fail = TD_FC_INVALID_POSITION; return false; }
     if (w.nt >= TD_CAP_TOWERS) { w.flags |= 2; w.fail = TD_FC_INVALID_POSITION; return false; }
     if (w.lane == 0) {
-        td_tower_rec &r = w.tw[w.nt];
+        td_tower_rec &r = w.tw()[w.nt];
         r.cd = 0.0;
         r.loc = (uint16_t)loc;
         r.type_lv = (uint8_t)t;
@@ -402,42 +422,45 @@ __device__ __forceinline__ bool tower_build(Ctx &w, int t, int loc, bool &map6_d
     return true;
 }
 
-__device__ __forceinline__ int find_tower(const Ctx &w, int loc)
+template <class W>
+__device__ __forceinline__ int find_tower(const W &w, int loc)
 {
-    bool m = w.lane < w.nt && w.tw[w.lane].loc == loc;
+    bool m = w.lane < w.nt && w.tw()[w.lane].loc == loc;
     unsigned b = __ballot_sync(kFull, m);
     return b ? __ffs(b) - 1 : -1;
 }
 
-__device__ __forceinline__ bool tower_lvup(Ctx &w, int loc)                              // TDBoard.py:249-271
+template <class W>
+__device__ __forceinline__ bool tower_lvup(W &w, int loc)                              // TDBoard.py:249-271
 {
     int idx = find_tower(w, loc);
     if (idx < 0) { w.fail = TD_FC_UNKNOWN_TARGET; return false; }
-    int tl = w.tw[idx].type_lv, ty = tl & 3, lv = tl >> 2;
+    int tl = w.tw()[idx].type_lv, ty = tl & 3, lv = tl >> 2;
     if (lv >= TD_NLV - 1) { w.fail = TD_FC_LV_MAX; return false; }
     const double cost = cc.tower_cost[ty][lv + 1];
     if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
     __syncwarp();
-    if (w.lane == 0) w.tw[idx].type_lv = (uint8_t)(ty | ((lv + 1) << 2));
+    if (w.lane == 0) w.tw()[idx].type_lv = (uint8_t)(ty | ((lv + 1) << 2));
     __syncwarp();
     w.cost_def = __dsub_rn(w.cost_def, cost);
     w.fail = TD_FC_SUCCESS;
     return true;
 }
 
-__device__ __forceinline__ bool tower_destruct(Ctx &w, int loc, bool &map6_dirty)        // TDBoard.py:273-293
+template <class W>
+__device__ __forceinline__ bool tower_destruct(W &w, int loc, bool &map6_dirty)        // TDBoard.py:273-293
 {
     int idx = find_tower(w, loc);
     if (idx < 0) { w.fail = TD_FC_UNKNOWN_TARGET; return false; }
-    int tl = w.tw[idx].type_lv;
+    int tl = w.tw()[idx].type_lv;
     double c = __dadd_rn(w.cost_def, __dmul_rn(cc.tower_refund[tl & 3][tl >> 2], cc.destruct_return));
     w.cost_def = cc.max_cost < c ? cc.max_cost : c;
     // remove from the list, keeping the order of the rest
     td_tower_rec mine;
     bool mv = w.lane > idx && w.lane < w.nt;
-    if (mv) mine = w.tw[w.lane];
+    if (mv) mine = w.tw()[w.lane];
     __syncwarp();
-    if (mv) w.tw[w.lane - 1] = mine;
+    if (mv) w.tw()[w.lane - 1] = mine;
     __syncwarp();
     w.nt -= 1;
     diamond_add(w, loc, -1);
@@ -447,14 +470,15 @@ __device__ __forceinline__ bool tower_destruct(Ctx &w, int loc, bool &map6_dirty
 }
 
 // Discrete action (TDDefense.py:61-77, TDMulti.py:100-115).  Returns success.
-__device__ __forceinline__ bool decode_discrete(Ctx &w, long long a, long long &real, int &failcode, bool &dirty)
+template <class W>
+__device__ __forceinline__ bool decode_discrete(W &w, long long a, long long &real, int &failcode, bool &dirty)
 {
-    const long long nop = 6ll * w.ncells;
+    const long long nop = 6ll * w.ncells();
     real = nop;
     failcode = 0;
     if (w.def_cd != 0 || a == nop || (unsigned long long)a > (unsigned long long)nop) return false;
     int ai = (int)a;
-    int act = ai / w.ncells, loc = ai - act * w.ncells;
+    int act = ai / w.ncells(), loc = ai - act * w.ncells();
     bool res;
     if (act < TD_NTYPES) res = tower_build(w, act, loc, dirty);
     else if (act == TD_NTYPES) res = tower_lvup(w, loc);
@@ -469,14 +493,15 @@ __device__ __forceinline__ bool decode_discrete(Ctx &w, long long a, long long &
 // screened per pass; a cell is skipped when none of its flagged operations can succeed in the
 // current state (no tower on it, and no flagged build that is both affordable and placeable).  The
 // screen is recomputed after every success because cost and map6 then change.
-__device__ __forceinline__ void decode_multi(Ctx &w, const long long *act, long long *real, bool &dirty)
+template <class W>
+__device__ __forceinline__ void decode_multi(W &w, const long long *act, long long *real, bool &dirty)
 {
-    const int cells = w.ncells;
-    uint8_t *tower_at = w.scratch;      // cells bytes: 1 where a tower stands (scratch >= cells_pad here)
+    const int cells = w.ncells();
+    uint8_t *tower_at = w.scratch();      // cells bytes: 1 where a tower stands (scratch >= cells_pad here)
     const bool enabled = w.def_cd == 0;
-    for (int q = w.lane; q < (w.cells_pad >> 2); q += 32) reinterpret_cast<uint32_t *>(tower_at)[q] = 0u;
+    for (int q = w.lane; q < (w.cells_pad() >> 2); q += 32) reinterpret_cast<uint32_t *>(tower_at)[q] = 0u;
     __syncwarp();
-    if (w.lane < w.nt) tower_at[w.tw[w.lane].loc] = 1;
+    if (w.lane < w.nt) tower_at[w.tw()[w.lane].loc] = 1;
     __syncwarp();
     for (int base = 0; base < cells; base += 32) {
         const int cell = base + w.lane;
@@ -496,7 +521,7 @@ __device__ __forceinline__ void decode_multi(Ctx &w, const long long *act, long 
                 bool can = false;
                 if (flags) {
                     if (tower_at[cell]) can = (flags & 0x30u) != 0 || false;
-                    if (!can && (flags & 0x0fu) && w.map6[cell] == 0) {
+                    if (!can && (flags & 0x0fu) && w.map6()[cell] == 0) {
 #pragma unroll
                         for (int t = 0; t < TD_NTYPES; ++t)
                             can = can || (((flags >> t) & 1u) && !(w.cost_def < cc.tower_cost[t][0]));
@@ -530,11 +555,12 @@ __device__ __forceinline__ void decode_multi(Ctx &w, const long long *act, long 
 // ------------------------------------------------------------------------------------------------
 // (b) summon
 
-__device__ __forceinline__ void append_enemy(Ctx &w, int t, int lv, int start)
+template <class W>
+__device__ __forceinline__ void append_enemy(W &w, int t, int lv, int start)
 {
     if (w.ne >= w.ecap) { w.flags |= 1; return; }
     if (w.lane == 0) {
-        td_enemy_rec &e = w.en[w.ne];
+        td_enemy_rec &e = w.en()[w.ne];
         e.LP = cc.enemy_LP[t][lv];
         e.margin = 0.0;
         e.loc = (uint16_t)start;
@@ -546,9 +572,10 @@ __device__ __forceinline__ void append_enemy(Ctx &w, int t, int lv, int start)
 
 // TDBoard.py:199-224 for one road.  `mine` is this lane's slot value (lanes road*8..road*8+7 hold the
 // cluster); updated in place to the RealAction value.  Returns the bool of the (bool, list) tuple.
-__device__ __forceinline__ bool summon_cluster(Ctx &w, int road, long long &mine, int lane_base)
+template <class W>
+__device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, int lane_base)
 {
-    const int start = w.mh->start[road];
+    const int start = w.mh()->start[road];
     const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
     bool tried = false, summoned = false;
 #pragma unroll 1
@@ -573,9 +600,10 @@ __device__ __forceinline__ bool summon_cluster(Ctx &w, int road, long long &mine
 // scripted attacker of the defender env: 8 x type t on one road (TDGymBasic.py:95-108 -> TDBoard.py:199-224).
 // All eight slots cost the same, so the first unaffordable slot ends the cluster; the summoned enemies are
 // appended by eight lanes at once.
-__device__ __forceinline__ void summon_uniform(Ctx &w, int t, int road)
+template <class W>
+__device__ __forceinline__ void summon_uniform(W &w, int t, int road)
 {
-    const int start = w.mh->start[road];
+    const int start = w.mh()->start[road];
     const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
     const double cost = cc.enemy_cost[t][lv];
     int n = 0;
@@ -588,7 +616,7 @@ __device__ __forceinline__ void summon_uniform(Ctx &w, int t, int road)
     w.fail = n == 0 ? TD_FC_COST_SHORTAGE : TD_FC_SUCCESS;
     if (n > w.ecap - w.ne) { w.flags |= 1; n = w.ecap - w.ne; }
     if (w.lane < n) {
-        td_enemy_rec &e = w.en[w.ne + w.lane];
+        td_enemy_rec &e = w.en()[w.ne + w.lane];
         e.LP = cc.enemy_LP[t][lv];
         e.margin = 0.0;
         e.loc = (uint16_t)start;
@@ -602,26 +630,28 @@ __device__ __forceinline__ void summon_uniform(Ctx &w, int t, int road)
 // ------------------------------------------------------------------------------------------------
 // scripted opponents on the device generator (TDGymBasic.py:81-196, random_agent=True)
 
-__device__ __forceinline__ void opponent_enemy(Ctx &w, int difficulty)
+template <class W>
+__device__ __forceinline__ void opponent_enemy(W &w, int difficulty)
 {
     if (w.atk_cd != 0) return;
     if (difficulty == 0) {                                   // random_enemy_lv0
         long long mine = 0;
         for (int k = 0; k < TD_CLUSTER; ++k) { int t = py_randbelow(w, TD_NTYPES + 1); if (w.lane == k) mine = t; }
-        int road = py_randbelow(w, w.mh->num_roads);
+        int road = py_randbelow(w, w.mh()->num_roads);
         summon_cluster(w, road, mine, 0);
     } else {                                                 // random_enemy_lv1
         int t = py_randbelow(w, TD_NTYPES);
-        int road = py_randbelow(w, w.mh->num_roads);
+        int road = py_randbelow(w, w.mh()->num_roads);
         summon_uniform(w, t, road);
     }
     w.atk_cd = cc.atk_interval;                              // the returned tuple is always truthy
 }
 
-__device__ __forceinline__ void opponent_tower(Ctx &w, int difficulty, bool &dirty)
+template <class W>
+__device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty)
 {
     if (w.def_cd != 0) return;
-    const int L = w.L;
+    const int L = w.L();
     if (difficulty == 0) {                                   // random_tower_lv0
         int r = py_randbelow(w, L), c = py_randbelow(w, L), t = py_randbelow(w, TD_NTYPES);
         if (tower_build(w, t, r * L + c, dirty)) w.def_cd = cc.def_interval;
@@ -630,11 +660,11 @@ __device__ __forceinline__ void opponent_tower(Ctx &w, int difficulty, bool &dir
     int act = py_randbelow(w, 3);                            // random_tower_lv1
     if (act == 0) {
         // road cells in row-major order
-        uint16_t *list = reinterpret_cast<uint16_t *>(w.scratch);
+        uint16_t *list = reinterpret_cast<uint16_t *>(w.scratch());
         int n = 0;
-        for (int base = 0; base < w.ncells; base += 32) {
+        for (int base = 0; base < w.ncells(); base += 32) {
             int c = base + w.lane;
-            bool on = c < w.ncells && (w.cells[c] & 1);
+            bool on = c < w.ncells() && (w.cells()[c] & 1);
             unsigned b = __ballot_sync(kFull, on);
             if (on) list[n + __popc(b & ((1u << w.lane) - 1u))] = (uint16_t)c;
             n += __popc(b);
@@ -658,7 +688,7 @@ __device__ __forceinline__ void opponent_tower(Ctx &w, int difficulty, bool &dir
         if (w.nt == 0) return;
         if (act == 2 && py_random(w) > .01) return;
         int id = py_randbelow(w, w.nt);
-        int loc = w.tw[id].loc;
+        int loc = w.tw()[id].loc;
         bool ok = act == 1 ? tower_lvup(w, loc) : tower_destruct(w, loc, dirty);
         if (ok) w.def_cd = cc.def_interval;
     }
@@ -673,18 +703,18 @@ struct EnemyRegs {
     bool valid;
 };
 
-template <int NCHUNK>
-__device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_out)
+template <int NCHUNK, class W>
+__device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_out)
 {
-    const int L = w.L, lane = w.lane;
+    const int L = w.L(), lane = w.lane;
     double reward = __dadd_rn(0.0, cc.reward_time);
     w.steps += 1;
     const double progress = (double)w.steps / (double)cc.max_steps;
 
     const int ne = w.ne, nt = w.nt;
     EnemyRegs E[NCHUNK];
-    double *keys = reinterpret_cast<double *>(w.scratch);    // [64]
-    uint8_t *erow = w.scratch + 512, *ecol = w.scratch + 576;  // [64] each
+    double *keys = reinterpret_cast<double *>(w.scratch());    // [64]
+    uint8_t *erow = w.scratch() + 512, *ecol = w.scratch() + 576;  // [64] each
 
     // ---- load enemies into registers, sort key = dist - margin (TDBoard.py:305)
     bool unsorted = false;
@@ -693,9 +723,9 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
         int e = lane + 32 * k;
         E[k].valid = e < ne;
         if (E[k].valid) {
-            const td_enemy_rec &x = w.en[e];
+            const td_enemy_rec &x = w.en()[e];
             E[k].LP = x.LP; E[k].margin = x.margin; E[k].loc = x.loc; E[k].tl = x.type_lv; E[k].slow = x.slowdown;
-            keys[e] = __dsub_rn((double)w.dist[E[k].loc], E[k].margin);
+            keys[e] = __dsub_rn((double)w.dist()[E[k].loc], E[k].margin);
         }
     }
     __syncwarp();
@@ -723,7 +753,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
 #pragma unroll
         for (int k = 0; k < NCHUNK; ++k)
             if (E[k].valid) {
-                td_enemy_rec &x = w.en[rank[k]];
+                td_enemy_rec &x = w.en()[rank[k]];
                 x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
                 x.slowdown = (uint8_t)E[k].slow;
             }
@@ -732,7 +762,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
         for (int k = 0; k < NCHUNK; ++k) {
             int e = lane + 32 * k;
             if (E[k].valid) {
-                const td_enemy_rec &x = w.en[e];
+                const td_enemy_rec &x = w.en()[e];
                 E[k].LP = x.LP; E[k].margin = x.margin; E[k].loc = x.loc; E[k].tl = x.type_lv; E[k].slow = x.slowdown;
             }
         }
@@ -750,9 +780,9 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
     // ---- towers choose targets: first enemy in list order within Chebyshev range, corpses included
     //      (TDBoard.py:306-312, TDElements.py:72-132).  Positions do not change inside the tower loop, so
     //      every tower's choice is independent: lane = tower.
-    uint8_t *fire = w.scratch + 640, *vict = w.scratch + 672;     // [32] each
+    uint8_t *fire = w.scratch() + 640, *vict = w.scratch() + 672;     // [32] each
     if (lane < nt) {
-        td_tower_rec &T = w.tw[lane];
+        td_tower_rec &T = w.tw()[lane];
         const int ty = T.type_lv & 3, lv = T.type_lv >> 2;
         double cd = __dsub_rn(T.cd, 1.0);
         int target = -1, victim = -1;
@@ -796,7 +826,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
         for (int t = 0; t < nt; ++t) {
             const int f = fire[t];
             if (f == 0xff) continue;
-            const int tl = w.tw[t].type_lv, ty = tl & 3, lv = tl >> 2;
+            const int tl = w.tw()[t].type_lv, ty = tl & 3, lv = tl >> 2;
             const double atk = cc.tower_attack[ty][lv];
             const double floor_ = __dmul_rn(atk, .05);
             const bool magic = (ty == 1 || ty == 3);
@@ -825,7 +855,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
 
     // ---- remove the killed, move the rest, remove the leaked (TDBoard.py:313-346)
     int kills = 0, leaks = 0, kept_before = 0;
-    const int end = w.mh->end;
+    const int end = w.mh()->end;
     int newidx[NCHUNK];
     bool keep[NCHUNK];
     __syncwarp();
@@ -839,7 +869,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
             else E[k].margin = __dadd_rn(E[k].margin, speed);
             while (E[k].margin >= 1.0) {
                 E[k].margin = __dsub_rn(E[k].margin, 1.0);
-                int d = (w.cells[E[k].loc] >> 4) & 3;
+                int d = (w.cells()[E[k].loc] >> 4) & 3;
                 E[k].loc += (d == 0) ? 1 : (d == 1) ? -1 : (d == 2) ? L : -L;
                 if (E[k].loc == end) { leaked = true; break; }
             }
@@ -854,7 +884,7 @@ __device__ __forceinline__ double board_step(Ctx &w, int &kills_out, int &leaks_
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k)
         if (keep[k]) {
-            td_enemy_rec &x = w.en[newidx[k]];
+            td_enemy_rec &x = w.en()[newidx[k]];
             x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
             x.slowdown = (uint8_t)E[k].slow;
         }
@@ -914,15 +944,16 @@ __device__ __forceinline__ void store_run(float4 *p, float v, int lane)
 
 // CELLS > 0: compile-time board size (runs of equal planes are unrolled stores with immediate offsets).
 // CELLS == 0: run-time board size, plane by plane (also handles L*L not divisible by 4).
-template <int CELLS>
-__device__ __forceinline__ void write_obs(Ctx &w, float *o)
+template <class W>
+__device__ __forceinline__ void write_obs(W &w, float *o)
 {
-    const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells;
+    constexpr int CELLS = W::kCells;
+    const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells();
     const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-    const float maxd = (float)w.mh->maxd_p1;
+    const float maxd = (float)w.mh()->maxd_p1;
     // The 12 broadcast values (f64 quotients rounded once to f32, TDBoard.py:115-125,134-142), one per lane:
     // lane 0 -> plane 5, 1 -> 11, 2 -> 12, 3 -> 13, 4..7 -> 41..44 (cost_def / enemy_cost / 8), 8..11 -> 21..24.
-    float *pv = reinterpret_cast<float *>(w.scratch) + 64;         // [48], behind ratio[64]
+    float *pv = reinterpret_cast<float *>(w.scratch()) + 64;         // [48], behind ratio[64]
     {
         double num = 0.0, den = 1.0;
         int plane = 47;
@@ -948,9 +979,9 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
         constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
         constexpr int kIters = (C4 + 31) / 32;
         float4 *o4 = reinterpret_cast<float4 *>(o);
-        const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells);
-        const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist);
-        const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6);
+        const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
+        const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
+        const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
             const int q = lane + 32 * it;
@@ -981,9 +1012,9 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
     } else if (vec) {
         const int c4 = cells >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(o);
-        const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells);
-        const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist);
-        const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6);
+        const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
+        const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
+        const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
         for (int q = lane; q < c4; q += 32) {
             uchar4 c = cb[q];
 #pragma unroll
@@ -1012,37 +1043,40 @@ __device__ __forceinline__ void write_obs(Ctx &w, float *o)
         for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
     } else {
         for (int q = lane; q < cells; q += 32) {
-            uint8_t c = w.cells[q];
+            uint8_t c = w.cells()[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k) TD_ST(o + (size_t)k * cells + q, (float)((c >> k) & 1));
-            TD_ST(o + (size_t)9 * cells + q, __fdiv_rn((float)w.dist[q], maxd));
-            TD_ST(o + (size_t)14 * cells + q, w.map6[q] == 0 ? 1.f : 0.f);
+            TD_ST(o + (size_t)9 * cells + q, __fdiv_rn((float)w.dist()[q], maxd));
+            TD_ST(o + (size_t)14 * cells + q, w.map6()[q] == 0 ? 1.f : 0.f);
         }
         for (int k = 4; k < TD_NCHANNELS; ++k)
             if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], lane);
     }
 
     // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
-    float *ratio = reinterpret_cast<float *>(w.scratch);       // [64]
+    float *ratio = reinterpret_cast<float *>(w.scratch());       // [64]
     const int ne = w.ne;
     for (int e = lane; e < ne; e += 32) {
-        const td_enemy_rec &x = w.en[e];
+        const td_enemy_rec &x = w.en()[e];
         ratio[e] = (float)(x.LP / cc.enemy_LP[x.type_lv & 3][x.type_lv >> 2]);
     }
     __syncwarp();   // also orders the dense stores above before the sparse stores below
-    if (lane == 0) o[(size_t)4 * cells + w.mh->end] = 1.f;
-    if (lane < w.mh->num_roads) o[(size_t)(6 + lane) * cells + w.mh->start[lane]] = 1.f;
+#ifdef TD_EXP_NO_SPARSE
+    return;
+#endif
+    if (lane == 0) o[(size_t)4 * cells + w.mh()->end] = 1.f;
+    if (lane < w.mh()->num_roads) o[(size_t)(6 + lane) * cells + w.mh()->start[lane]] = 1.f;
     if (lane < w.nt) {
-        const td_tower_rec &T = w.tw[lane];
+        const td_tower_rec &T = w.tw()[lane];
         o[(size_t)(15 + (T.type_lv >> 2)) * cells + T.loc] = 1.f;
         o[(size_t)(17 + (T.type_lv & 3)) * cells + T.loc] = 1.f;
     }
     for (int e = lane; e < ne; e += 32) {
-        const int loc = w.en[e].loc, ty = w.en[e].type_lv & 3;
+        const int loc = w.en()[e].loc, ty = w.en()[e].type_lv & 3;
         float mn = 1.f, mx = 0.f, sum = 0.f, cnt = 0.f;
         bool leader = true;
         for (int j = 0; j < ne; ++j) {
-            if (w.en[j].loc == loc && (w.en[j].type_lv & 3) == ty) {
+            if (w.en()[j].loc == loc && (w.en()[j].type_lv & 3) == ty) {
                 if (j < e) leader = false;
                 float r = ratio[j];
                 mn = r < mn ? r : mn;
@@ -1075,21 +1109,20 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
-    uint8_t *const slice = td_smem + (size_t)warp * p.smem_per_warp;     // [record | scratch]
-    uint8_t *rec = p.records + (size_t)env * p.record_bytes;
+    Ctx<CELLS> w;
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);                // [record | scratch]
+    uint8_t *rec = p.records + (size_t)env * w.record_bytes();
     const td_step_io &io = p.io;
     const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
                                  !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
     // the record and the inputs are requested together: one round trip
-    issue_env_load(slice, p, rec, lane);
+    issue_env_load(w, rec);
     long long in_def = 0, atk_mine = TD_NTYPES;
     int in_opp = 0xff;
     if (KIND != TD_KIND_ATK && !MULTI) in_def = io.def_action_dev[env];
     if (KIND != TD_KIND_DEF && lane < TD_ROADS * TD_CLUSTER)
         atk_mine = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane];
     if (KIND == TD_KIND_DEF && io.opponent_dev != nullptr) in_opp = io.opponent_dev[env];
-    Ctx w;
-    ctx_bind(w, slice, slice + p.record_bytes, p);
     w.ecap = 32 * NCHUNK;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
@@ -1100,15 +1133,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     w.atk_cd = max(w.atk_cd - 1, 0);
     w.def_cd = max(w.def_cd - 1, 0);
 
-    long long real_def = 6ll * w.ncells;
+    long long real_def = 6ll * w.ncells();
     int fail_def = 0;
     bool def_ok = false;
     int fail_atk[TD_ROADS] = {0, 0, 0}, n_fail_atk = 0;
 
     auto defender = [&]() {
         if (MULTI) {
-            decode_multi(w, reinterpret_cast<const long long *>(io.def_action_dev) + (size_t)env * 6 * w.ncells,
-                         io.real_def_dev ? reinterpret_cast<long long *>(io.real_def_dev) + (size_t)env * 6 * w.ncells : nullptr,
+            decode_multi(w, reinterpret_cast<const long long *>(io.def_action_dev) + (size_t)env * 6 * w.ncells(),
+                         io.real_def_dev ? reinterpret_cast<long long *>(io.real_def_dev) + (size_t)env * 6 * w.ncells() : nullptr,
                          dirty);
         } else {
             def_ok = decode_discrete(w, in_def, real_def, fail_def, dirty);
@@ -1116,7 +1149,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     };
     auto attacker = [&]() {
         if (w.atk_cd == 0) {
-            const int nr = w.mh->num_roads;
+            const int nr = w.mh()->num_roads;
             for (int i = 0; i < nr; ++i) {
                 if (!(KIND == TD_KIND_2P && MULTI)) {
                     bool skip = __all_sync(kFull, (lane < i * 8 || lane >= i * 8 + 8) || atk_mine == TD_NTYPES);
@@ -1137,7 +1170,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         if (io.opponent_dev != nullptr) {
             const int o = in_opp;
             if (o != 0xff && w.atk_cd == 0) {
-                summon_uniform(w, o & 3, min((o >> 4) & 3, w.mh->num_roads - 1));
+                summon_uniform(w, o & 3, min((o >> 4) & 3, w.mh()->num_roads - 1));
                 w.atk_cd = cc.atk_interval;
             }
         } else if (device_opponent) opponent_enemy(w, p.difficulty);
@@ -1173,7 +1206,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
             int4 f = make_int4(n_fail_atk, fail_atk[0], fail_atk[1], fail_atk[2]);
             reinterpret_cast<int4 *>(io.fail_atk_dev)[env] = f;
         }
-        td_env_header *h = w.hdr;
+        td_env_header *h = w.hdr();
         h->ep_return = __dadd_rn(h->ep_return, reward);
         h->ep_kills = (uint16_t)(h->ep_kills + kills);
         h->ep_leaks = (uint16_t)(h->ep_leaks + leaks);
@@ -1194,8 +1227,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     __syncwarp();
 
     if (done && io.auto_reset) {
-        int next = (w.hdr->map_id + p.map_stride) % p.n_maps;
-        if (lane == 0) w.hdr->episode += 1;
+        int next = (w.hdr()->map_id + p.map_stride) % p.n_maps;
+        if (lane == 0) w.hdr()->episode += 1;
         reset_env(w, p, next, true);
         dirty = true;
     }
@@ -1206,9 +1239,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         w.cn = min(kRngCache, max(kMtWords - w.mt_pos, 0));
         if (lane < w.cn) asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word) : "l"(w.mt + w.mt_pos + lane) : "memory");
     }
-    if (io.obs_dev) write_obs<CELLS>(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells);
+    if (io.obs_dev) write_obs(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
     __syncwarp();
-    if (w.mt != nullptr && lane < kRngCache) const_cast<uint32_t *>(w.rng_cache)[lane] = next_word;
+    if (w.mt != nullptr && lane < kRngCache) const_cast<uint32_t *>(w.rng_cache())[lane] = next_word;
     store_env(w, p, rec, dirty);
 }
 
@@ -1220,16 +1253,16 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
     if (mask && !mask[env]) return;
-    Ctx w;
-    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, td_smem + (size_t)warp * p.smem_per_warp + p.record_bytes, p);
+    Ctx<0> w;
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     uint8_t *rec = p.records + (size_t)env * p.record_bytes;
-    if (w.lane < (kHdrBytes >> 4)) reinterpret_cast<int4 *>(w.hdr)[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
+    if (w.lane < (kHdrBytes >> 4)) reinterpret_cast<int4 *>(w.hdr())[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
     __syncwarp();
     pull_header(w);
     int id = map_ids ? map_ids[env] : env % p.n_maps;
     id = ((id % p.n_maps) + p.n_maps) % p.n_maps;
     reset_env(w, p, id, true);
-    if (obs) write_obs<0>(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+    if (obs) write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells());
     __syncwarp();
     store_env(w, p, rec, true);
 }
@@ -1240,10 +1273,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const Ste
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
-    Ctx w;
-    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, td_smem + (size_t)warp * p.smem_per_warp + p.record_bytes, p);
+    Ctx<CELLS> w;
+    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     load_env(w, p, p.records + (size_t)env * p.record_bytes);
-    write_obs<CELLS>(w, obs + (size_t)env * TD_NCHANNELS * w.ncells);
+    write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells());
 }
 
 // deterministic reduction of the per-env statistics: one block, fixed order

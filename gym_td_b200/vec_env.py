@@ -20,6 +20,41 @@ from . import engine as E
 from . import mapgen, params
 
 
+class _Info(dict):
+    """Lazy info dict: RealAction / Win / FailCode are tensor views, AllowNextMove is computed on access."""
+
+    def __init__(self, env):
+        super().__init__()
+        k = env.kind
+        self._allow = env._allow
+        self._kind = k
+        self["Win"] = env.win
+        if k == "def":
+            self["RealAction"], self["FailCode"] = env.real_def, env.fail_def
+        elif k == "atk":
+            self["RealAction"], self["FailCode"] = env.real_atk, env.fail_atk
+        else:
+            self["RealAction"] = {"Attacker": env.real_atk, "Defender": env.real_def}
+            self["FailCode"] = {"Attacker": env.fail_atk, "Defender": env.fail_def}
+        self["AllowNextMoveBits"] = env._allow          # bit0 defender, bit1 attacker
+
+    def __missing__(self, key):
+        if key != "AllowNextMove":
+            raise KeyError(key)
+        a = self._allow
+        if self._kind == "def":
+            v = (a & 1).bool()
+        elif self._kind == "atk":
+            v = (a & 2).bool()
+        else:
+            v = {"Attacker": (a & 2).bool(), "Defender": (a & 1).bool()}
+        self[key] = v
+        return v
+
+    def __contains__(self, key):
+        return key == "AllowNextMove" or dict.__contains__(self, key)
+
+
 class TDVecEnv(object):
     def __init__(self, kind, map_size, num_envs, seed=0, device=0, difficulty=1, auto_reset=True, env_offset=0,
                  n_maps=None, scripted_opponent=True, multi_action=None, cfg=None, mapgen_threads=None):
@@ -109,17 +144,9 @@ class TDVecEnv(object):
         return self.obs, self.reward, self._done.view(torch.bool), self.info()
 
     def info(self):
-        allow = self._allow
-        inf = {"Win": self.win}
-        if self.kind == "def":
-            inf.update(RealAction=self.real_def, AllowNextMove=(allow & 1).bool(), FailCode=self.fail_def)
-        elif self.kind == "atk":
-            inf.update(RealAction=self.real_atk, AllowNextMove=(allow & 2).bool(), FailCode=self.fail_atk)
-        else:
-            inf.update(RealAction={"Attacker": self.real_atk, "Defender": self.real_def},
-                       AllowNextMove={"Attacker": (allow & 2).bool(), "Defender": (allow & 1).bool()},
-                       FailCode={"Attacker": self.fail_atk, "Defender": self.fail_def})
-        return inf
+        """info dict of the last step.  Values are views of the output tensors; the AllowNextMove masks are
+        derived from the packed bits only when they are read (no extra kernels on the step path)."""
+        return _Info(self)
 
     # -- host-buffer path (what a numpy-facing gym caller uses) ------------------------------------
     def _host_buffers(self):
