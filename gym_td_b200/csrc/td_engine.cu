@@ -375,7 +375,8 @@ extern "C" int td_set_map_stride(td_handle *h, int stride)
 extern "C" int td_set_difficulty(td_handle *h, int difficulty)
 {
     if (!h) return TD_E_INVALID;
-    if (difficulty < 0 || difficulty > 1) return fail(h, TD_E_INVALID, "on-device scripted opponents exist for difficulty 0 and 1");
+    const int top = h->kind == TD_KIND_ATK ? 2 : 1;      // random_enemy_lv0/1, random_tower_lv0/1/2 (TDGymBasic.py:81-292)
+    if (difficulty < 0 || difficulty > top) return fail(h, TD_E_INVALID, "no scripted opponent of that level for this env kind");
     h->difficulty = difficulty;
     return TD_OK;
 }

@@ -570,29 +570,47 @@ __device__ __forceinline__ void append_enemy(W &w, int t, int lv, int start)
     w.ne += 1;
 }
 
-// TDBoard.py:199-224 for one road.  `mine` is this lane's slot value (lanes road*8..road*8+7 hold the
+// TDBoard.py:199-224 for one road.  `mine` is this lane's slot value (lanes lane_base..lane_base+7 hold the
 // cluster); updated in place to the RealAction value.  Returns the bool of the (bool, list) tuple.
+// The eight types are packed into three ballots, the f64 cost chain runs on uniform registers, and the
+// affordable slots append their enemies in one parallel store (list order = slot order).
 template <class W>
 __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, int lane_base)
 {
     const int start = w.mh()->start[road];
     const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
-    bool tried = false, summoned = false;
-#pragma unroll 1
-    for (int k = 0; k < TD_CLUSTER; ++k) {
-        long long t = __shfl_sync(kFull, mine, lane_base + k);
-        if (t < 0 || t >= TD_NTYPES) continue;               // 4 == enemy_types: empty slot
-        tried = true;
-        const double cost = cc.enemy_cost[(int)t][lv];
-        if (w.cost_atk < cost) {
-            if (w.lane == lane_base + k) mine = TD_NTYPES;
-        } else {
-            w.cost_atk = __dsub_rn(w.cost_atk, cost);
-            append_enemy(w, (int)t, lv, start);
-            summoned = true;
+    const int tv = (mine < 0 || mine >= TD_NTYPES) ? TD_NTYPES : (int)mine;     // 4 == enemy_types: empty slot
+    const unsigned b0 = __ballot_sync(kFull, tv & 1) >> lane_base, b1 = __ballot_sync(kFull, tv & 2) >> lane_base,
+                   b2 = __ballot_sync(kFull, tv & 4) >> lane_base;
+    unsigned todo = ~b2 & 0xffu;                     // slots holding a real type (0..3)
+    const bool tried = todo != 0;
+    unsigned ok = 0, poor = 0;
+    while (todo) {
+        const int k = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int t = ((b0 >> k) & 1) | (((b1 >> k) & 1) << 1);
+        const double cost = cc.enemy_cost[t][lv];
+        if (w.cost_atk < cost) poor |= 1u << k;
+        else { w.cost_atk = __dsub_rn(w.cost_atk, cost); ok |= 1u << k; }
+    }
+    int n = __popc(ok);
+    if (n > w.ecap - w.ne) { w.flags |= 1; n = w.ecap - w.ne; }
+    const int k = w.lane - lane_base;
+    if (k >= 0 && k < TD_CLUSTER) {
+        if ((poor >> k) & 1u) mine = TD_NTYPES;
+        const int idx = __popc(ok & ((1u << k) - 1u));
+        if (((ok >> k) & 1u) && idx < n) {
+            td_enemy_rec &e = w.en()[w.ne + idx];
+            e.LP = cc.enemy_LP[tv][lv];
+            e.margin = 0.0;
+            e.loc = (uint16_t)start;
+            e.type_lv = (uint8_t)(tv | (lv << 2));
+            e.slowdown = 0;
         }
     }
-    if (!summoned && tried) { w.fail = TD_FC_COST_SHORTAGE; return false; }
+    w.ne += n;
+    __syncwarp();
+    if (ok == 0 && tried) { w.fail = TD_FC_COST_SHORTAGE; return false; }
     w.fail = TD_FC_SUCCESS;
     return true;
 }
@@ -657,8 +675,33 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
         if (tower_build(w, t, r * L + c, dirty)) w.def_cd = cc.def_interval;
         return;
     }
-    int act = py_randbelow(w, 3);                            // random_tower_lv1
+    int act = py_randbelow(w, 3);                            // random_tower_lv1 / lv2
     if (act == 0) {
+        int t = 0;
+        if (difficulty == 2) {
+            // TDGymBasic.py:216-240: counter the enemy type drawn in proportion to the live enemies
+            if (w.ne == 0) return;
+            int cnt[TD_NTYPES] = {0, 0, 0, 0};
+            for (int base = 0; base < w.ne; base += 32) {
+                const int e = base + w.lane;
+                const int ty = e < w.ne ? (w.en()[e].type_lv & 3) : -1;
+#pragma unroll
+                for (int q = 0; q < TD_NTYPES; ++q) cnt[q] += __popc(__ballot_sync(kFull, ty == q));
+            }
+            double p = py_random(w);
+            int pick = -1, last = 0;
+#pragma unroll
+            for (int q = 0; q < TD_NTYPES; ++q) {
+                if (cnt[q] == 0 || pick >= 0) continue;
+                const double ratio = (double)(float)cnt[q] / (double)w.ne;   // float32 counts / np.int64 sum -> f64
+                last = q;
+                if (p < ratio) pick = q;
+                else p = __dsub_rn(p, ratio);
+            }
+            if (pick < 0) pick = last;
+            t = pick == 0 ? 2 : pick == 2 ? 1 : 0;           // [2, 0, 1, 0][type]
+            if (py_random(w) < 0.2) t = 3;
+        }
         // road cells in row-major order
         uint16_t *list = reinterpret_cast<uint16_t *>(w.scratch());
         int n = 0;
@@ -675,7 +718,7 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
             if (w.lane == 0) { uint16_t t = list[i]; list[i] = list[j]; list[j] = t; }
         }
         __syncwarp();
-        int t = py_randbelow(w, TD_NTYPES);
+        if (difficulty != 2) t = py_randbelow(w, TD_NTYPES);
         for (int k = 0; k < n; ++k) {
             int di = py_randbelow(w, 25);
             int cell = list[k];

@@ -256,9 +256,8 @@ class TDAttack(TDGymBasic):
         self.action_space = spaces.Box(low=0, high=config.enemy_types,
                                        shape=(hyper_parameters.max_num_of_roads, hyper_parameters.max_cluster_length),
                                        dtype=np.int64)
-        if difficulty not in (0, 1):
-            raise NotImplementedError("scripted defender level %r is not on the device yet (levels 0 and 1 are)"
-                                      % (difficulty,))
+        if difficulty not in (0, 1, 2):
+            raise AttributeError("'TDAttack' object has no attribute 'random_tower_lv%s'" % (difficulty,))
         if not random_agent:
             raise NotImplementedError("TDAttack(random_agent=False) raises in the reference (TDGymBasic.py:191); "
                                       "use random_agent=True and random.seed()")

@@ -23,8 +23,7 @@ def _state_dict(eng, rec, base_none):
 
 
 def _replayable(path):
-    t = GU.Traj(path)
-    return not (t.kind == "atk" and t.meta["difficulty"] == 2)
+    return True
 
 
 @pytest.mark.parametrize("path", [p for p in GU.trajectories() if _replayable(p)],

@@ -31,6 +31,11 @@ def test_atk_opponent_lv0():
 
 
 @pytest.mark.parametrize("L", [10, 20, 30])
+def test_atk_opponent_lv2(L):
+    assert PU.run_parity("atk", L, n_envs=24, steps=900, seed=L + 6, opponent="device", difficulty=2) > 2000
+
+
+@pytest.mark.parametrize("L", [10, 20, 30])
 def test_multi_discrete(L):
     assert PU.run_parity("2p", L, n_envs=32, steps=1200, seed=L + 3, opponent="none") > 3000
 
