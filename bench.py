@@ -143,7 +143,7 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     if CB.reference_available() and not multi:
         kind_name = "reference"
-        per_worker = 400                       # env-steps per worker per bench step (~60 ms of Python)
+        per_worker = 1000                      # env-steps per worker per bench step (~0.15 s of Python)
         pool = CB.ReferencePool(cores)
         for _ in range(max(args.warmup, 1)):
             pool.run(kind, L, per_worker)
