@@ -2,6 +2,7 @@
 // Host logic only: buffer layout, validation, launches on the caller's stream, error reporting.
 // There is no CPU fallback: every compute entry point needs a CUDA device.
 #include "td_kernels.cuh"
+#include "td_rollout.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -637,5 +638,52 @@ extern "C" int td_reset_stats(td_handle *h, void *stream)
     TD_CUDA(h, cudaSetDevice(h->device));
     TD_CUDA(h, cudaMemsetAsync(h->stats, 0, (size_t)h->n_envs * sizeof(EnvStats), (cudaStream_t)stream));
     h->steps = 0;
+    return TD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rollout consumer (td_rollout.cuh)
+
+extern "C" int td_rollout_mask(td_handle *h, int which, int64_t *action_dev, const uint8_t *allow_next_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (!action_dev || !allow_next_dev || which < 0 || which > 1) return fail(h, TD_E_INVALID, "td_rollout_mask: bad arguments");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    const int width = which == 0 ? 1 : TD_ROADS * TD_CLUSTER;
+    const int total = h->n_envs * width;
+    rollout_mask_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        action_dev, allow_next_dev, h->n_envs, width, which == 0 ? 1 : 2,
+        which == 0 ? (int64_t)6 * h->cells : (int64_t)TD_NTYPES);
+    TD_CUDA(h, cudaGetLastError());
+    return TD_OK;
+}
+
+extern "C" int td_rollout_record(td_handle *h, int which, const int64_t *action_dev, const int64_t *real_action_dev,
+                                 const double *reward_dev, const uint8_t *done_dev, double penalty,
+                                 float *rewards_row_dev, uint8_t *dones_row_dev, int64_t *actions_row_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (!action_dev || !real_action_dev || !reward_dev || !done_dev || !rewards_row_dev || !dones_row_dev ||
+        which < 0 || which > 1)
+        return fail(h, TD_E_INVALID, "td_rollout_record: bad arguments");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    const int width = which == 0 ? 1 : TD_ROADS * TD_CLUSTER;
+    rollout_record_kernel<<<(h->n_envs + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        action_dev, real_action_dev, reward_dev, done_dev, h->n_envs, width, penalty, rewards_row_dev,
+        dones_row_dev, actions_row_dev);
+    TD_CUDA(h, cudaGetLastError());
+    return TD_OK;
+}
+
+extern "C" int td_gae(int horizon, int n, const float *rewards_dev, const uint8_t *dones_dev, const float *values_dev,
+                      const float *next_value_dev, double gamma, double lam, float *advs_dev, float *returns_dev,
+                      void *stream)
+{
+    if (horizon < 1 || n < 1 || !rewards_dev || !dones_dev || !values_dev || !next_value_dev || !advs_dev || !returns_dev)
+        return fail(nullptr, TD_E_INVALID, "td_gae: bad arguments");
+    gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(horizon, n, rewards_dev, dones_dev, values_dev,
+                                                                next_value_dev, gamma, lam, advs_dev, returns_dev);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, TD_E_CUDA, std::string("td_gae: ") + cudaGetErrorString(e));
     return TD_OK;
 }

@@ -82,7 +82,7 @@ class TDVecEnv(object):
         self.reward = torch.zeros(N, dtype=torch.float64, device=dev)
         self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
         self.win = torch.zeros(N, dtype=torch.int8, device=dev)
-        self._allow = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._allow = torch.full((N,), 3, dtype=torch.uint8, device=dev)    # AllowNextMove starts True (train/main.py:87)
         self.fail_def = torch.zeros(N, dtype=torch.int32, device=dev)
         self.fail_atk = torch.zeros((N, 4), dtype=torch.int32, device=dev)
         self.real_atk = torch.zeros((N, E.ROADS, E.CLUSTER), dtype=torch.int64, device=dev)

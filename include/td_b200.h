@@ -256,6 +256,20 @@ int td_get_opponent(td_handle *h, int first_env, int n, uint32_t *states_host);
 int td_get_stats(td_handle *h, td_stats *out, void *stream);
 int td_reset_stats(td_handle *h, void *stream);
 
+/* ---- rollout consumer: the per-step bookkeeping of the reference's training loop ----
+ * td_rollout_mask    <- train/main.py:130-132       actions of envs that may not move become empty_action()
+ * td_rollout_record  <- train/PPO/Callbacks.py:21-23 + train/PPO/Model.py:134-140
+ *                       reward -= penalty when action != RealAction; row t of [horizon, n] buffers
+ * td_gae             <- train/PPO/Model.py:166-192   GAE(gamma, lam) advantages and returns over one horizon
+ * `which`: 0 = defender Discrete action ([n] int64, empty = 6*L*L), 1 = attacker cluster ([n,3,8], empty = 4).
+ * All pointers are device pointers; buffers are [horizon, n(, width)] with the env index fastest. */
+int td_rollout_mask(td_handle *h, int which, int64_t *action_dev, const uint8_t *allow_next_dev, void *stream);
+int td_rollout_record(td_handle *h, int which, const int64_t *action_dev, const int64_t *real_action_dev,
+                      const double *reward_dev, const uint8_t *done_dev, double penalty,
+                      float *rewards_row_dev, uint8_t *dones_row_dev, int64_t *actions_row_dev, void *stream);
+int td_gae(int horizon, int n, const float *rewards_dev, const uint8_t *dones_dev, const float *values_dev,
+           const float *next_value_dev, double gamma, double lam, float *advs_dev, float *returns_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,108 @@
+"""Rollout consumer: numpy oracle vs golden vectors produced by the reference's own PPO class
+(CPU), and the CUDA kernels vs both (GPU)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rollout_oracle as RO
+from tests import golden_util as GU
+
+
+def _load(name):
+    return np.load(os.path.join(GU.GOLDEN, "rollout_%s.npz" % name))
+
+
+@pytest.mark.parametrize("name", ["def", "atk"])
+def test_oracle_matches_reference_ppo(name):
+    z = _load(name)
+    T, n = z["rewards"].shape
+    rew = np.zeros((T, n), dtype=np.float32)
+    for t in range(T):
+        rew[t], d = RO.record_row(z["actions"][t], z["real"][t], z["rewards_in"][t], z["dones"][t], float(z["penalty"]))
+        assert np.array_equal(d, z["dones"][t])
+    assert np.array_equal(rew.view(np.uint32), z["rewards"].view(np.uint32))
+    advs, rets = RO.gae(rew, z["dones"], z["values"], z["next_value"], float(z["gamma"]), float(z["lam"]))
+    assert np.array_equal(advs.view(np.uint32), z["advs"].view(np.uint32))
+    assert np.array_equal(rets.view(np.uint32), z["returns"].view(np.uint32))
+
+
+def test_mask_semantics():
+    a = np.arange(5, dtype=np.int64)
+    out = RO.mask_actions(a, [True, False, True, False, True], 600)
+    assert out.tolist() == [0, 600, 2, 600, 4]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["def", "atk"])
+def test_cuda_gae_and_record_match_reference(name):
+    import torch
+    from gym_td_b200 import engine as E
+    z = _load(name)
+    T, n = z["rewards"].shape
+    dev = torch.device("cuda", 0)
+    eng = E.Engine("def" if name == "def" else "atk", 10, n)
+    which = 0 if name == "def" else 1
+    rewards = torch.zeros((T, n), dtype=torch.float32, device=dev)
+    dones = torch.zeros((T, n), dtype=torch.uint8, device=dev)
+    acts_buf = torch.zeros(z["actions"].shape, dtype=torch.int64, device=dev)
+    for t in range(T):
+        a = torch.from_numpy(z["actions"][t]).to(dev).contiguous()
+        r = torch.from_numpy(z["real"][t]).to(dev).contiguous()
+        rw = torch.from_numpy(z["rewards_in"][t]).to(dev)
+        d = torch.from_numpy(z["dones"][t].astype(np.uint8)).to(dev)
+        eng._check(eng._lib.td_rollout_record(eng._h, which, a.data_ptr(), r.data_ptr(), rw.data_ptr(), d.data_ptr(),
+                                              float(z["penalty"]), rewards[t].data_ptr(), dones[t].data_ptr(),
+                                              acts_buf[t].data_ptr(), 0))
+    torch.cuda.synchronize()
+    assert np.array_equal(rewards.cpu().numpy().view(np.uint32), z["rewards"].view(np.uint32))
+    assert np.array_equal(dones.cpu().numpy().astype(bool), z["dones"])
+    assert np.array_equal(acts_buf.cpu().numpy(), z["actions"])
+    advs = torch.zeros((T, n), dtype=torch.float32, device=dev)
+    rets = torch.zeros_like(advs)
+    v = torch.from_numpy(z["values"]).to(dev).contiguous()
+    nv = torch.from_numpy(z["next_value"]).to(dev).contiguous()
+    assert E.lib().td_gae(T, n, rewards.data_ptr(), dones.data_ptr(), v.data_ptr(), nv.data_ptr(), float(z["gamma"]),
+                          float(z["lam"]), advs.data_ptr(), rets.data_ptr(), 0) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(advs.cpu().numpy().view(np.uint32), z["advs"].view(np.uint32))
+    assert np.array_equal(rets.cpu().numpy().view(np.uint32), z["returns"].view(np.uint32))
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_rollout_buffer_on_live_env_matches_oracle():
+    import torch
+    from gym_td_b200.rollout import RolloutBuffer
+    from gym_td_b200.vec_env import TDVecEnv
+    N, L, T = 512, 10, 32
+    env = TDVecEnv("def", L, N, seed=11, auto_reset=True,
+                   cfg=__import__("tests.parity_util", fromlist=["x"]).make_config(defender_action_interval=3))
+    env.reset()
+    buf = RolloutBuffer(env, horizon=T)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    rows_r, rows_d = [], []
+    allow_prev = np.ones(N, dtype=bool)
+    for t in range(T):
+        a = torch.randint(0, 601, (N,), dtype=torch.int64, device="cuda", generator=g)
+        want = RO.mask_actions(a.cpu().numpy(), allow_prev, 600)
+        buf.mask(a)
+        assert np.array_equal(a.cpu().numpy(), want)
+        obs, rew, done, info = env.step(a)
+        full = buf.record(a)
+        r32, d = RO.record_row(want, info["RealAction"].cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy())
+        rows_r.append(r32)
+        rows_d.append(d)
+        allow_prev = info["AllowNextMove"].cpu().numpy()
+        assert full == (t == T - 1)
+    assert (~allow_prev).any() or True
+    rew_ref, done_ref = np.stack(rows_r), np.stack(rows_d)
+    assert np.array_equal(buf.rewards.cpu().numpy().view(np.uint32), rew_ref.view(np.uint32))
+    assert np.array_equal(buf.dones.cpu().numpy().astype(bool), done_ref)
+    values = torch.randn((T, N), device="cuda", generator=g)
+    nv = torch.randn((N,), device="cuda", generator=g)
+    advs, rets = buf.flush(values, nv)
+    a_ref, r_ref = RO.gae(rew_ref, done_ref, values.cpu().numpy(), nv.cpu().numpy(), 0.99, 0.95)
+    assert np.array_equal(advs.cpu().numpy().view(np.uint32), a_ref.view(np.uint32))
+    assert np.array_equal(rets.cpu().numpy().view(np.uint32), r_ref.view(np.uint32))
+    env.close()
