@@ -191,28 +191,36 @@ static size_t smem_of(const td_handle *h) { return (size_t)kWarpsPerCta * h->sme
 
 // The step kernel is specialised on (env kind, multi-action) x (board size, enemy chunks): 10x10 boards hold at
 // most 32 live enemies (one per lane), larger boards 64; other sizes take the run-time-size variant.
+#ifndef TD_GROUP_SMALL
+#define TD_GROUP_SMALL 32     // lanes per game instance on 10x10 boards.  16 (two instances per warp) is
+                              // correct and makes the rules 10 % faster, but the full step 6 % slower on B200:
+                              // twice as many open observation streams per SM lower the store efficiency.
+#endif
+
+static int step_group_width(const td_handle *h) { return h->L == 10 ? TD_GROUP_SMALL : 32; }
+
 static int step_variant(int kind, bool multi)
 {
     return kind == TD_KIND_DEF ? (multi ? 1 : 0) : kind == TD_KIND_ATK ? 2 : (multi ? 4 : 3);
 }
 
-template <int CELLS, int NCHUNK, typename F> static cudaError_t for_each_kind(F f)
+template <int CELLS, int NCHUNK, int GW, typename F> static cudaError_t for_each_kind(F f)
 {
     cudaError_t e;
-    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK>)) != cudaSuccess) return e;
-    if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK>)) != cudaSuccess) return e;
-    if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK>)) != cudaSuccess) return e;
-    if ((e = f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK>)) != cudaSuccess) return e;
-    return f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK>);
+    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
+    return f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK, GW>);
 }
 
 template <typename F> static cudaError_t for_each_step_kernel(const td_handle *h, F f)
 {
     switch (h->L) {
-    case 10: return for_each_kind<100, 1>(f);
-    case 20: return for_each_kind<400, 2>(f);
-    case 30: return for_each_kind<900, 2>(f);
-    default: return for_each_kind<0, 2>(f);
+    case 10: return for_each_kind<100, 32 / TD_GROUP_SMALL, TD_GROUP_SMALL>(f);     // 32 live enemies
+    case 20: return for_each_kind<400, 2, 32>(f);
+    case 30: return for_each_kind<900, 2, 32>(f);
+    default: return for_each_kind<0, 2, 32>(f);
     }
 }
 
@@ -257,8 +265,9 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     if (rc != TD_OK) return bail(rc);
     if ((e = cudaSetDevice(device)) != cudaSuccess) { h->err = cudaGetErrorString(e); return bail(TD_E_CUDA); }
     size_t smem = smem_of(h);
-    if (smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
-    if ((e = for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, smem); })) != cudaSuccess ||
+    const size_t step_smem = smem * (32 / step_group_width(h));          // instances per CTA x slice
+    if (step_smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
+    if ((e = for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
         (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel<0>, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel<100>, smem)) != cudaSuccess ||
@@ -509,8 +518,14 @@ extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
     StepParams p;
     fill_params(h, p);
     p.io = *io;
-    const int grid = grid_of(h), block = kWarpsPerCta * 32;
-    const size_t smem = smem_of(h);
+    const int per_cta = kWarpsPerCta * 32 / step_group_width(h);         // game instances per CTA
+    const int grid = (h->n_envs + per_cta - 1) / per_cta, block = kWarpsPerCta * 32;
+    size_t smem = (size_t)per_cta * h->smem_per_warp;
+    static const int pad_kb = getenv("TD_STEP_SMEM_KB") ? atoi(getenv("TD_STEP_SMEM_KB")) : 0;   // experiments
+    if (pad_kb > 0 && (size_t)pad_kb * 1024 > smem) {
+        smem = (size_t)pad_kb * 1024;
+        for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, smem); });
+    }
     cudaStream_t s = (cudaStream_t)stream;
     const int want = step_variant(h->kind, io->multi_action != 0);
     int seen = 0;

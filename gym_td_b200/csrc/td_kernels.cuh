@@ -109,15 +109,20 @@ struct StepParams {
 
 // CELLS > 0: board size known at compile time -> every pointer into the slice is base + constant.
 // CELLS == 0: layout read from the kernel parameters (constant bank).
-template <int CELLS>
+// GW = lanes per game instance: 32 (one warp per env) or 16 (two envs per warp: the uniform bookkeeping
+// of both is issued once, and twice as many envs are in flight per SM at the same warp count).
+template <int CELLS, int GW>
 struct Ctx {
     static constexpr int kCells = CELLS;
+    static constexpr int G = GW;
+    unsigned gmask;            // the warp lanes of this env's group
+    int gbase;                 // first warp lane of the group
     static constexpr int kL = CELLS == 100 ? 10 : CELLS == 400 ? 20 : CELLS == 900 ? 30 : 0;
     static constexpr int kPad = (CELLS + 15) & ~15;
     uint8_t *slice;            // the warp's shared-memory slice: [record | scratch]
     const StepParams *pp;
-    int lane, ecap;
-    // uniform copies of hot header fields (identical in all lanes)
+    int lane, ecap;            // lane = index inside the group
+    // uniform copies of hot header fields (identical in all lanes of the group)
     double cost_def, cost_atk;
     int nt, ne, base_LP, steps, def_cd, atk_cd, fail, flags;
     // opponent generator cursor
@@ -146,26 +151,42 @@ struct Ctx {
     __device__ __forceinline__ uint8_t *scratch() const { return slice + record_bytes(); }
 };
 
-__device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16, int lane)
+// group-level primitives: ballots are returned relative to the group (bit 0 = group lane 0)
+template <class W> __device__ __forceinline__ unsigned gballot(const W &w, bool pred)
+{
+    const unsigned b = __ballot_sync(w.gmask, pred);
+    if (W::G == 32) return b;
+    return (b >> w.gbase) & 0xffffu;
+}
+template <class W, class T> __device__ __forceinline__ T gshfl(const W &w, T v, int src)
+{
+    return __shfl_sync(w.gmask, v, src, W::G);
+}
+template <class W> __device__ __forceinline__ bool gall(const W &w, bool pred) { return __all_sync(w.gmask, pred); }
+template <class W> __device__ __forceinline__ bool gany(const W &w, bool pred) { return __any_sync(w.gmask, pred); }
+template <class W> __device__ __forceinline__ void gsync(const W &w) { __syncwarp(w.gmask); }
+
+__device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16, int lane, int stride)
 {
     int4 *d = reinterpret_cast<int4 *>(dst);
     const int4 *s = reinterpret_cast<const int4 *>(src);
-    for (int q = lane; q < n16; q += 32) d[q] = s[q];
+    for (int q = lane; q < n16; q += stride) d[q] = s[q];
 }
 
 // global -> shared, 16 bytes per lane per instruction, asynchronous (LDGSTS): every segment of a stage
 // is in flight at once and no register is held while the data travels.
-__device__ __forceinline__ void async_copy16(void *smem_dst, const void *gmem_src, int n16, int lane)
+__device__ __forceinline__ void async_copy16(void *smem_dst, const void *gmem_src, int n16, int lane, int stride)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     const char *s = reinterpret_cast<const char *>(gmem_src);
-    for (int q = lane; q < n16; q += 32)
+    for (int q = lane; q < n16; q += stride)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * q), "l"(s + 16 * q) : "memory");
 }
-__device__ __forceinline__ void async_wait_all()
+template <class W>
+__device__ __forceinline__ void async_wait_all(const W &w)
 {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    gsync(w);
 }
 
 template <class W>
@@ -173,7 +194,10 @@ __device__ __forceinline__ void ctx_bind(W &w, uint8_t *slice, const StepParams 
 {
     w.slice = slice;
     w.pp = &p;
-    w.lane = threadIdx.x & 31;
+    const int wl = threadIdx.x & 31;
+    w.lane = wl & (W::G - 1);
+    w.gbase = wl - w.lane;
+    w.gmask = W::G == 32 ? kFull : (0xffffu << w.gbase);
     w.ecap = TD_CAP_ENEMIES;
     w.mt = nullptr;
     w.win = 0; w.mt_pos = 0; w.win_k = 0; w.win_n = 0;
@@ -184,7 +208,7 @@ __device__ __forceinline__ void ctx_bind(W &w, uint8_t *slice, const StepParams 
 template <class W>
 __device__ __forceinline__ void load_static_map(W &w, const StepParams &p, int map_id)
 {
-    async_copy16(w.mh(), p.maps + (size_t)map_id * w.map_bytes(), w.map_bytes() >> 4, w.lane);
+    async_copy16(w.mh(), p.maps + (size_t)map_id * w.map_bytes(), w.map_bytes() >> 4, w.lane, W::G);
     w.static_dirty = true;
 }
 
@@ -231,25 +255,25 @@ __device__ __forceinline__ void push_header(W &w)
 
 // Regenerate the 624 words in place.  mt[k] = mt[(k+397)%624] ^ f(mt[k], mt[k+1]); chunks of 32 words in
 // ascending order keep every operand in the state (old / new) the sequential algorithm sees.
-__device__ __noinline__ void mt_twist(uint32_t *mt, int lane)
+__device__ __noinline__ void mt_twist(uint32_t *mt, int lane, int stride, unsigned gmask)
 {
 #pragma unroll 1
-    for (int base = 0; base < kMtWords; base += 32) {
+    for (int base = 0; base < kMtWords; base += stride) {
         const int k = base + lane;
         uint32_t v = 0;
         if (k < kMtWords - 1) {
             uint32_t y = (mt[k] & 0x80000000u) | (mt[k + 1] & 0x7fffffffu);
             v = mt[k < 227 ? k + 397 : k - 227] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
         }
-        __syncwarp();
+        __syncwarp(gmask);
         if (k < kMtWords - 1) mt[k] = v;
-        __syncwarp();
+        __syncwarp(gmask);
     }
     if (lane == 0) {
         uint32_t y = (mt[623] & 0x80000000u) | (mt[0] & 0x7fffffffu);
         mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
     }
-    __syncwarp();
+    __syncwarp(gmask);
 }
 
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
@@ -266,7 +290,7 @@ template <class W>
 __device__ __forceinline__ void mt_fill_window(W &w)
 {
     int n = kMtWords - w.mt_pos;
-    w.win_n = n < 32 ? (n < 0 ? 0 : n) : 32;
+    w.win_n = n < W::G ? (n < 0 ? 0 : n) : W::G;
     w.win_k = 0;
     w.win = w.lane < w.win_n ? w.mt[w.mt_pos + w.lane] : 0u;
 }
@@ -281,10 +305,10 @@ __device__ __forceinline__ uint32_t mt_next(W &w)
         return r;
     }
     if (w.win_k == w.win_n) {
-        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane); w.mt_pos = 0; }
+        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane, W::G, w.gmask); w.mt_pos = 0; }
         mt_fill_window(w);
     }
-    uint32_t r = mt_temper(__shfl_sync(kFull, w.win, w.win_k));
+    uint32_t r = mt_temper(gshfl(w, w.win, w.win_k));
     ++w.win_k;
     ++w.mt_pos;
     return r;
@@ -295,8 +319,8 @@ __device__ __forceinline__ uint32_t mt_next(W &w)
 template <class W>
 __device__ __forceinline__ void issue_env_load(W &w, const uint8_t *rec)
 {
-    async_copy16(w.slice, rec, (w.off_towers() + kSpecTowers * kTowerBytes) >> 4, w.lane);
-    async_copy16(w.en(), rec + w.off_enemies(), (kSpecEnemies * kEnemyBytes) >> 4, w.lane);
+    async_copy16(w.slice, rec, (w.off_towers() + kSpecTowers * kTowerBytes) >> 4, w.lane, W::G);
+    async_copy16(w.en(), rec + w.off_enemies(), (kSpecEnemies * kEnemyBytes) >> 4, w.lane, W::G);
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
@@ -308,11 +332,11 @@ __device__ __forceinline__ void finish_env_load(W &w, const StepParams &p, const
     w.mt = mt_base;
     if (w.nt > kSpecTowers || w.ne > kSpecEnemies) {
         if (w.nt > kSpecTowers)
-            async_copy16(w.tw() + kSpecTowers, rec + w.off_towers() + kSpecTowers * kTowerBytes, w.nt - kSpecTowers, w.lane);
+            async_copy16(w.tw() + kSpecTowers, rec + w.off_towers() + kSpecTowers * kTowerBytes, w.nt - kSpecTowers, w.lane, W::G);
         if (w.ne > kSpecEnemies)
             async_copy16(w.en() + kSpecEnemies, rec + w.off_enemies() + kSpecEnemies * kEnemyBytes,
-                         ((w.ne - kSpecEnemies) * 3 + 1) >> 1, w.lane);
-        async_wait_all();
+                         ((w.ne - kSpecEnemies) * 3 + 1) >> 1, w.lane, W::G);
+        async_wait_all(w);
     }
 }
 
@@ -320,7 +344,7 @@ template <class W>
 __device__ __forceinline__ void load_env(W &w, const StepParams &p, const uint8_t *rec, uint32_t *mt_base = nullptr)
 {
     issue_env_load(w, rec);
-    async_wait_all();
+    async_wait_all(w);
     finish_env_load(w, p, rec, mt_base);
 }
 
@@ -329,11 +353,11 @@ template <class W>
 __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
 {
     push_header(w);
-    __syncwarp();
+    gsync(w);
     const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : kHdrBytes);
-    warp_copy16(rec, w.slice, head >> 4, w.lane);
-    warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane);
-    warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane);
+    warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
+    warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane, W::G);
+    warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane, W::G);
 }
 
 // TDGymBasic.reset (:37-55) + TDBoard.__init__ (:63-79): fresh episode on map `map_id`.
@@ -341,11 +365,11 @@ template <class W>
 __device__ __forceinline__ void reset_env(W &w, const StepParams &p, int map_id, bool reload_map)
 {
     if (reload_map) {
-        __syncwarp();
+        gsync(w);
         load_static_map(w, p, map_id);
-        async_wait_all();
+        async_wait_all(w);
     }
-    for (int q = w.lane; q < (w.cells_pad() >> 2); q += 32) {
+    for (int q = w.lane; q < (w.cells_pad() >> 2); q += W::G) {
         uint32_t c4 = reinterpret_cast<const uint32_t *>(w.cells())[q];
         reinterpret_cast<uint32_t *>(w.map6())[q] = c4 & 0x01010101u;           // map[6] = 1 on road cells
     }
@@ -364,7 +388,7 @@ __device__ __forceinline__ void reset_env(W &w, const StepParams &p, int map_id,
         w.hdr()->ep_kills = 0;
         w.hdr()->ep_leaks = 0;
     }
-    __syncwarp();
+    gsync(w);
 }
 
 // random._randbelow_with_getrandbits(n), 1 <= n < 2^31
@@ -392,13 +416,13 @@ __device__ __forceinline__ void diamond_add(W &w, int loc, int delta)
 {
     const int L = w.L(), D = cc.tower_distance, WD = 2 * D + 1;
     const int r0 = loc / L, c0 = loc - r0 * L;
-    for (int k = w.lane; k < WD * WD; k += 32) {
+    for (int k = w.lane; k < WD * WD; k += W::G) {
         int i = k / WD - D, j = k % WD - D;
         int r = r0 + i, c = c0 + j;
         if (abs(i) + abs(j) <= D && r >= 0 && r < L && c >= 0 && c < L)
             w.map6()[r * L + c] = (uint8_t)(w.map6()[r * L + c] + delta);
     }
-    __syncwarp();
+    gsync(w);
 }
 
 template <class W>
@@ -425,9 +449,13 @@ __device__ __forceinline__ bool tower_build(W &w, int t, int loc, bool &map6_dir
 template <class W>
 __device__ __forceinline__ int find_tower(const W &w, int loc)
 {
-    bool m = w.lane < w.nt && w.tw()[w.lane].loc == loc;
-    unsigned b = __ballot_sync(kFull, m);
-    return b ? __ffs(b) - 1 : -1;
+    int idx = -1;
+    for (int base = 0; base < w.nt; base += W::G) {
+        const int t = base + w.lane;
+        const unsigned b = gballot(w, t < w.nt && w.tw()[t].loc == loc);
+        if (b && idx < 0) idx = base + __ffs(b) - 1;
+    }
+    return idx;
 }
 
 template <class W>
@@ -439,9 +467,9 @@ __device__ __forceinline__ bool tower_lvup(W &w, int loc)                       
     if (lv >= TD_NLV - 1) { w.fail = TD_FC_LV_MAX; return false; }
     const double cost = cc.tower_cost[ty][lv + 1];
     if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
-    __syncwarp();
+    gsync(w);
     if (w.lane == 0) w.tw()[idx].type_lv = (uint8_t)(ty | ((lv + 1) << 2));
-    __syncwarp();
+    gsync(w);
     w.cost_def = __dsub_rn(w.cost_def, cost);
     w.fail = TD_FC_SUCCESS;
     return true;
@@ -456,12 +484,20 @@ __device__ __forceinline__ bool tower_destruct(W &w, int loc, bool &map6_dirty) 
     double c = __dadd_rn(w.cost_def, __dmul_rn(cc.tower_refund[tl & 3][tl >> 2], cc.destruct_return));
     w.cost_def = cc.max_cost < c ? cc.max_cost : c;
     // remove from the list, keeping the order of the rest
-    td_tower_rec mine;
-    bool mv = w.lane > idx && w.lane < w.nt;
-    if (mv) mine = w.tw()[w.lane];
-    __syncwarp();
-    if (mv) w.tw()[w.lane - 1] = mine;
-    __syncwarp();
+    constexpr int kPasses = TD_CAP_TOWERS / W::G;
+    td_tower_rec mine[kPasses];
+#pragma unroll
+    for (int q = 0; q < kPasses; ++q) {
+        const int t = w.lane + W::G * q;
+        if (t > idx && t < w.nt) mine[q] = w.tw()[t];
+    }
+    gsync(w);
+#pragma unroll
+    for (int q = 0; q < kPasses; ++q) {
+        const int t = w.lane + W::G * q;
+        if (t > idx && t < w.nt) w.tw()[t - 1] = mine[q];
+    }
+    gsync(w);
     w.nt -= 1;
     diamond_add(w, loc, -1);
     map6_dirty = true;
@@ -499,11 +535,11 @@ __device__ __forceinline__ void decode_multi(W &w, const long long *act, long lo
     const int cells = w.ncells();
     uint8_t *tower_at = w.scratch();      // cells bytes: 1 where a tower stands (scratch >= cells_pad here)
     const bool enabled = w.def_cd == 0;
-    for (int q = w.lane; q < (w.cells_pad() >> 2); q += 32) reinterpret_cast<uint32_t *>(tower_at)[q] = 0u;
-    __syncwarp();
-    if (w.lane < w.nt) tower_at[w.tw()[w.lane].loc] = 1;
-    __syncwarp();
-    for (int base = 0; base < cells; base += 32) {
+    for (int q = w.lane; q < (w.cells_pad() >> 2); q += W::G) reinterpret_cast<uint32_t *>(tower_at)[q] = 0u;
+    gsync(w);
+    for (int t = w.lane; t < w.nt; t += W::G) tower_at[w.tw()[t].loc] = 1;
+    gsync(w);
+    for (int base = 0; base < cells; base += W::G) {
         const int cell = base + w.lane;
         unsigned flags = 0;          // bit ch set when action[ch][cell] == 1
         if (cell < cells) {
@@ -515,7 +551,7 @@ __device__ __forceinline__ void decode_multi(W &w, const long long *act, long lo
         }
         unsigned done_mask = 0;      // successes of this lane's cell
         if (enabled) {
-            unsigned pending = __ballot_sync(kFull, flags != 0);
+            unsigned pending = gballot(w, flags != 0);
             while (pending) {
                 // screen with the current state
                 bool can = false;
@@ -528,16 +564,16 @@ __device__ __forceinline__ void decode_multi(W &w, const long long *act, long lo
                     }
                     // a flagged build on a free cell can create the tower that a flagged LvUp/destruct then hits
                 }
-                unsigned cand = __ballot_sync(kFull, can) & pending;
+                unsigned cand = gballot(w, can) & pending;
                 if (!cand) break;
                 int src = __ffs(cand) - 1;
-                unsigned f = __shfl_sync(kFull, flags, src);
+                unsigned f = gshfl(w, flags, src);
                 int loc = base + src;
                 unsigned ok = 0;
                 for (int t = 0; t < TD_NTYPES; ++t)
-                    if ((f >> t) & 1u) if (tower_build(w, t, loc, dirty)) { ok |= 1u << t; if (w.lane == 0) tower_at[loc] = 1; __syncwarp(); }
+                    if ((f >> t) & 1u) if (tower_build(w, t, loc, dirty)) { ok |= 1u << t; if (w.lane == 0) tower_at[loc] = 1; gsync(w); }
                 if ((f >> 4) & 1u) if (tower_lvup(w, loc)) ok |= 1u << 4;
-                if ((f >> 5) & 1u) if (tower_destruct(w, loc, dirty)) { ok |= 1u << 5; if (w.lane == 0) tower_at[loc] = 0; __syncwarp(); }
+                if ((f >> 5) & 1u) if (tower_destruct(w, loc, dirty)) { ok |= 1u << 5; if (w.lane == 0) tower_at[loc] = 0; gsync(w); }
                 if (ok) w.def_cd = cc.def_interval;
                 if (w.lane == src) done_mask = ok;
                 // cells up to and including src are finished
@@ -549,7 +585,7 @@ __device__ __forceinline__ void decode_multi(W &w, const long long *act, long lo
             for (int ch = 0; ch < 6; ++ch) __stcs(real + (size_t)ch * cells + cell, (long long)((done_mask >> ch) & 1u));
         }
     }
-    __syncwarp();
+    gsync(w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -580,8 +616,8 @@ __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, 
     const int start = w.mh()->start[road];
     const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
     const int tv = (mine < 0 || mine >= TD_NTYPES) ? TD_NTYPES : (int)mine;     // 4 == enemy_types: empty slot
-    const unsigned b0 = __ballot_sync(kFull, tv & 1) >> lane_base, b1 = __ballot_sync(kFull, tv & 2) >> lane_base,
-                   b2 = __ballot_sync(kFull, tv & 4) >> lane_base;
+    const unsigned b0 = gballot(w, tv & 1) >> lane_base, b1 = gballot(w, tv & 2) >> lane_base,
+                   b2 = gballot(w, tv & 4) >> lane_base;
     unsigned todo = ~b2 & 0xffu;                     // slots holding a real type (0..3)
     const bool tried = todo != 0;
     unsigned ok = 0, poor = 0;
@@ -609,7 +645,7 @@ __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, 
         }
     }
     w.ne += n;
-    __syncwarp();
+    gsync(w);
     if (ok == 0 && tried) { w.fail = TD_FC_COST_SHORTAGE; return false; }
     w.fail = TD_FC_SUCCESS;
     return true;
@@ -642,7 +678,7 @@ __device__ __forceinline__ void summon_uniform(W &w, int t, int road)
         e.slowdown = 0;
     }
     w.ne += n;
-    __syncwarp();
+    gsync(w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -682,11 +718,11 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
             // TDGymBasic.py:216-240: counter the enemy type drawn in proportion to the live enemies
             if (w.ne == 0) return;
             int cnt[TD_NTYPES] = {0, 0, 0, 0};
-            for (int base = 0; base < w.ne; base += 32) {
+            for (int base = 0; base < w.ne; base += W::G) {
                 const int e = base + w.lane;
                 const int ty = e < w.ne ? (w.en()[e].type_lv & 3) : -1;
 #pragma unroll
-                for (int q = 0; q < TD_NTYPES; ++q) cnt[q] += __popc(__ballot_sync(kFull, ty == q));
+                for (int q = 0; q < TD_NTYPES; ++q) cnt[q] += __popc(gballot(w, ty == q));
             }
             double p = py_random(w);
             int pick = -1, last = 0;
@@ -705,19 +741,19 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
         // road cells in row-major order
         uint16_t *list = reinterpret_cast<uint16_t *>(w.scratch());
         int n = 0;
-        for (int base = 0; base < w.ncells(); base += 32) {
+        for (int base = 0; base < w.ncells(); base += W::G) {
             int c = base + w.lane;
             bool on = c < w.ncells() && (w.cells()[c] & 1);
-            unsigned b = __ballot_sync(kFull, on);
+            unsigned b = gballot(w, on);
             if (on) list[n + __popc(b & ((1u << w.lane) - 1u))] = (uint16_t)c;
             n += __popc(b);
         }
-        __syncwarp();
+        gsync(w);
         for (int i = n - 1; i >= 1; --i) {                   // random.shuffle
             int j = py_randbelow(w, i + 1);
             if (w.lane == 0) { uint16_t t = list[i]; list[i] = list[j]; list[j] = t; }
         }
-        __syncwarp();
+        gsync(w);
         if (difficulty != 2) t = py_randbelow(w, TD_NTYPES);
         for (int k = 0; k < n; ++k) {
             int di = py_randbelow(w, 25);
@@ -763,7 +799,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
     bool unsorted = false;
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) {
-        int e = lane + 32 * k;
+        int e = lane + W::G * k;
         E[k].valid = e < ne;
         if (E[k].valid) {
             const td_enemy_rec &x = w.en()[e];
@@ -771,14 +807,14 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
             keys[e] = __dsub_rn((double)w.dist()[E[k].loc], E[k].margin);
         }
     }
-    __syncwarp();
+    gsync(w);
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) {
-        int e = lane + 32 * k;
+        int e = lane + W::G * k;
         bool inv = E[k].valid && e > 0 && keys[e - 1] > keys[e];
         unsorted = unsorted || inv;
     }
-    unsorted = __any_sync(kFull, unsorted);
+    unsorted = gany(w, unsorted);
     if (unsorted) {
         // stable rank = #(key smaller) + #(equal key, earlier position)
         int rank[NCHUNK];
@@ -788,11 +824,11 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
             double kj = keys[j];
 #pragma unroll
             for (int k = 0; k < NCHUNK; ++k) {
-                int e = lane + 32 * k;
+                int e = lane + W::G * k;
                 if (E[k].valid) { double ke = keys[e]; rank[k] += (kj < ke || (kj == ke && j < e)) ? 1 : 0; }
             }
         }
-        __syncwarp();
+        gsync(w);
 #pragma unroll
         for (int k = 0; k < NCHUNK; ++k)
             if (E[k].valid) {
@@ -800,10 +836,10 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
                 x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
                 x.slowdown = (uint8_t)E[k].slow;
             }
-        __syncwarp();
+        gsync(w);
 #pragma unroll
         for (int k = 0; k < NCHUNK; ++k) {
-            int e = lane + 32 * k;
+            int e = lane + W::G * k;
             if (E[k].valid) {
                 const td_enemy_rec &x = w.en()[e];
                 E[k].LP = x.LP; E[k].margin = x.margin; E[k].loc = x.loc; E[k].tl = x.type_lv; E[k].slow = x.slowdown;
@@ -812,20 +848,20 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
     }
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) {
-        int e = lane + 32 * k;
+        int e = lane + W::G * k;
         if (E[k].valid) {
             E[k].r = E[k].loc / L; E[k].c = E[k].loc - E[k].r * L;
             erow[e] = (uint8_t)E[k].r; ecol[e] = (uint8_t)E[k].c;
         }
     }
-    __syncwarp();
+    gsync(w);
 
     // ---- towers choose targets: first enemy in list order within Chebyshev range, corpses included
     //      (TDBoard.py:306-312, TDElements.py:72-132).  Positions do not change inside the tower loop, so
     //      every tower's choice is independent: lane = tower.
     uint8_t *fire = w.scratch() + 640, *vict = w.scratch() + 672;     // [32] each
-    if (lane < nt) {
-        td_tower_rec &T = w.tw()[lane];
+    for (int tt = lane; tt < nt; tt += W::G) {
+        td_tower_rec &T = w.tw()[tt];
         const int ty = T.type_lv & 3, lv = T.type_lv >> 2;
         double cd = __dsub_rn(T.cd, 1.0);
         int target = -1, victim = -1;
@@ -853,10 +889,10 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
             if (cd < 0.0) cd = 0.0;
         }
         T.cd = cd;
-        fire[lane] = (uint8_t)(target < 0 ? 0xff : target);
-        vict[lane] = (uint8_t)(victim < 0 ? 0xff : victim);
+        fire[tt] = (uint8_t)(target < 0 ? 0xff : target);
+        vict[tt] = (uint8_t)(victim < 0 ? 0xff : victim);
     }
-    __syncwarp();
+    gsync(w);
 
     // ---- damage in tower order: lane = enemy (TDElements.py:19-28)
     bool hit[NCHUNK];
@@ -877,7 +913,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
             const int fr = erow[f], fc = ecol[f], v = vict[t];
 #pragma unroll
             for (int k = 0; k < NCHUNK; ++k) {
-                int e = lane + 32 * k;
+                int e = lane + W::G * k;
                 bool h;
                 if (ty == 2) h = E[k].valid && max(abs(E[k].r - fr), abs(E[k].c - fc)) <= sp;
                 else if (ty == 3) h = E[k].valid && e == v;
@@ -901,7 +937,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
     const int end = w.mh()->end;
     int newidx[NCHUNK];
     bool keep[NCHUNK];
-    __syncwarp();
+    gsync(w);
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k) {
         bool killed = E[k].valid && hit[k] && !(E[k].LP > 0.0);
@@ -918,7 +954,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
             }
         }
         keep[k] = E[k].valid && !killed && !leaked;
-        unsigned bk = __ballot_sync(kFull, killed), bl = __ballot_sync(kFull, leaked), bs = __ballot_sync(kFull, keep[k]);
+        unsigned bk = gballot(w, killed), bl = gballot(w, leaked), bs = gballot(w, keep[k]);
         kills += __popc(bk);
         leaks += __popc(bl);
         newidx[k] = kept_before + __popc(bs & ((1u << lane) - 1u));
@@ -932,7 +968,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
             x.slowdown = (uint8_t)E[k].slow;
         }
     w.ne = kept_before;
-    __syncwarp();
+    gsync(w);
 
     reward = __dadd_rn(reward, __dmul_rn(cc.reward_kill, (double)kills));
     const bool has_base = cc.base_LP >= 0;
@@ -959,30 +995,30 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
 // (f) observation: dense planes with streaming float4 stores, then the sparse one-hots / enemy
 //     statistics as 4-byte stores on top (ordered after the dense pass by __syncwarp).
 
-__device__ __forceinline__ void fill_planes(float *o, int first_plane, int n_planes, int cells, float v, int lane)
+__device__ __forceinline__ void fill_planes(float *o, int first_plane, int n_planes, int cells, float v, int lane, int stride)
 {
     float4 *p = reinterpret_cast<float4 *>(o + (size_t)first_plane * cells);
     const int n4 = (n_planes * cells) >> 2;
     const float4 x = make_float4(v, v, v, v);
-    for (int q = lane; q < n4; q += 32) TD_ST(p + q, x);
+    for (int q = lane; q < n4; q += stride) TD_ST(p + q, x);
 }
 
-__device__ __forceinline__ void fill_planes_scalar(float *o, int first_plane, int n_planes, int cells, float v, int lane)
+__device__ __forceinline__ void fill_planes_scalar(float *o, int first_plane, int n_planes, int cells, float v, int lane, int stride)
 {
     float *p = o + (size_t)first_plane * cells;
-    for (int q = lane; q < n_planes * cells; q += 32) TD_ST(p + q, v);
+    for (int q = lane; q < n_planes * cells; q += stride) TD_ST(p + q, v);
 }
 
 // N4 consecutive float4 of one value, fully unrolled: one STG.128 with an immediate offset per 512 bytes.
-template <int N4>
+template <int N4, int G>
 __device__ __forceinline__ void store_run(float4 *p, float v, int lane)
 {
     const float4 x = make_float4(v, v, v, v);
-    constexpr int kFullIters = N4 / 32, kRem = N4 % 32;
+    constexpr int kFullIters = N4 / G, kRem = N4 % G;
     p += lane;
 #pragma unroll
-    for (int k = 0; k < kFullIters; ++k) TD_ST(p + 32 * k, x);
-    if (kRem != 0 && lane < kRem) TD_ST(p + 32 * kFullIters, x);
+    for (int k = 0; k < kFullIters; ++k) TD_ST(p + G * k, x);
+    if (kRem != 0 && lane < kRem) TD_ST(p + G * kFullIters, x);
 }
 
 // CELLS > 0: compile-time board size (runs of equal planes are unrolled stores with immediate offsets).
@@ -1011,23 +1047,22 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
         float val = (float)qv;
         if (lane == 0 && cc.base_LP < 0) val = 1.f;
         if (lane >= 8 && lane < 12) val = w.cost_def >= cc.tower_cost[lane - 8][0] ? 1.f : 0.f;
-        __syncwarp();
-        pv[lane] = 0.f;
-        if (lane < 16) pv[32 + lane] = 0.f;
-        __syncwarp();
+        gsync(w);
+        for (int q = lane; q < 48; q += W::G) pv[q] = 0.f;
+        gsync(w);
         if (lane < 12) pv[plane] = val;
-        __syncwarp();
+        gsync(w);
     }
     if (CELLS > 0 && vec) {
         constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
-        constexpr int kIters = (C4 + 31) / 32;
+        constexpr int kIters = (C4 + W::G - 1) / W::G;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
         const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
         const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-            const int q = lane + 32 * it;
+            const int q = lane + W::G * it;
             if (q < C4) {
                 const uchar4 c = cb[q], d = db[q], m = mb[q];
 #pragma unroll
@@ -1040,52 +1075,52 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
                                                      m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
             }
         }
-        store_run<C4>(o4 + 4 * C4, 0.f, lane);
-        store_run<C4>(o4 + 5 * C4, pv[5], lane);
-        store_run<3 * C4>(o4 + 6 * C4, 0.f, lane);
-        store_run<C4>(o4 + 10 * C4, 0.f, lane);
+        store_run<C4, W::G>(o4 + 4 * C4, 0.f, lane);
+        store_run<C4, W::G>(o4 + 5 * C4, pv[5], lane);
+        store_run<3 * C4, W::G>(o4 + 6 * C4, 0.f, lane);
+        store_run<C4, W::G>(o4 + 10 * C4, 0.f, lane);
 #pragma unroll
-        for (int k = 11; k < 14; ++k) store_run<C4>(o4 + k * C4, pv[k], lane);
-        store_run<6 * C4>(o4 + 15 * C4, 0.f, lane);
+        for (int k = 11; k < 14; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
+        store_run<6 * C4, W::G>(o4 + 15 * C4, 0.f, lane);
 #pragma unroll
-        for (int k = 21; k < 25; ++k) store_run<C4>(o4 + k * C4, pv[k], lane);
-        store_run<16 * C4>(o4 + 25 * C4, 0.f, lane);
+        for (int k = 21; k < 25; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
+        store_run<16 * C4, W::G>(o4 + 25 * C4, 0.f, lane);
 #pragma unroll
-        for (int k = 41; k < 45; ++k) store_run<C4>(o4 + k * C4, pv[k], lane);
+        for (int k = 41; k < 45; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
     } else if (vec) {
         const int c4 = cells >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
         const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
         const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
-        for (int q = lane; q < c4; q += 32) {
+        for (int q = lane; q < c4; q += W::G) {
             uchar4 c = cb[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 TD_ST(o4 + k * c4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
                                                     (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
         }
-        fill_planes(o, 4, 1, cells, 0.f, lane);
-        fill_planes(o, 5, 1, cells, pv[5], lane);
-        fill_planes(o, 6, 3, cells, 0.f, lane);
-        for (int q = lane; q < c4; q += 32) {
+        fill_planes(o, 4, 1, cells, 0.f, lane, W::G);
+        fill_planes(o, 5, 1, cells, pv[5], lane, W::G);
+        fill_planes(o, 6, 3, cells, 0.f, lane, W::G);
+        for (int q = lane; q < c4; q += W::G) {
             uchar4 d = db[q];
             TD_ST(o4 + 9 * c4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
                                                 __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
         }
-        fill_planes(o, 10, 1, cells, 0.f, lane);
-        for (int k = 11; k < 14; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
-        for (int q = lane; q < c4; q += 32) {
+        fill_planes(o, 10, 1, cells, 0.f, lane, W::G);
+        for (int k = 11; k < 14; ++k) fill_planes(o, k, 1, cells, pv[k], lane, W::G);
+        for (int q = lane; q < c4; q += W::G) {
             uchar4 m = mb[q];
             TD_ST(o4 + 14 * c4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
                                                  m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
         }
-        fill_planes(o, 15, 6, cells, 0.f, lane);
-        for (int k = 21; k < 25; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
-        fill_planes(o, 25, 16, cells, 0.f, lane);
-        for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], lane);
+        fill_planes(o, 15, 6, cells, 0.f, lane, W::G);
+        for (int k = 21; k < 25; ++k) fill_planes(o, k, 1, cells, pv[k], lane, W::G);
+        fill_planes(o, 25, 16, cells, 0.f, lane, W::G);
+        for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], lane, W::G);
     } else {
-        for (int q = lane; q < cells; q += 32) {
+        for (int q = lane; q < cells; q += W::G) {
             uint8_t c = w.cells()[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k) TD_ST(o + (size_t)k * cells + q, (float)((c >> k) & 1));
@@ -1093,28 +1128,28 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
             TD_ST(o + (size_t)14 * cells + q, w.map6()[q] == 0 ? 1.f : 0.f);
         }
         for (int k = 4; k < TD_NCHANNELS; ++k)
-            if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], lane);
+            if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], lane, W::G);
     }
 
     // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
     float *ratio = reinterpret_cast<float *>(w.scratch());       // [64]
     const int ne = w.ne;
-    for (int e = lane; e < ne; e += 32) {
+    for (int e = lane; e < ne; e += W::G) {
         const td_enemy_rec &x = w.en()[e];
         ratio[e] = (float)(x.LP / cc.enemy_LP[x.type_lv & 3][x.type_lv >> 2]);
     }
-    __syncwarp();   // also orders the dense stores above before the sparse stores below
+    gsync(w);   // also orders the dense stores above before the sparse stores below
 #ifdef TD_EXP_NO_SPARSE
     return;
 #endif
     if (lane == 0) o[(size_t)4 * cells + w.mh()->end] = 1.f;
     if (lane < w.mh()->num_roads) o[(size_t)(6 + lane) * cells + w.mh()->start[lane]] = 1.f;
-    if (lane < w.nt) {
-        const td_tower_rec &T = w.tw()[lane];
+    for (int t = lane; t < w.nt; t += W::G) {
+        const td_tower_rec &T = w.tw()[t];
         o[(size_t)(15 + (T.type_lv >> 2)) * cells + T.loc] = 1.f;
         o[(size_t)(17 + (T.type_lv & 3)) * cells + T.loc] = 1.f;
     }
-    for (int e = lane; e < ne; e += 32) {
+    for (int e = lane; e < ne; e += W::G) {
         const int loc = w.en()[e].loc, ty = w.en()[e].type_lv & 3;
         float mn = 1.f, mx = 0.f, sum = 0.f, cnt = 0.f;
         bool leader = true;
@@ -1146,29 +1181,34 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 #define TD_MIN_BLOCKS 6
 #endif
 
-template <int KIND, bool MULTI, int CELLS, int NCHUNK>
+template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const StepParams p)
 {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * kWarpsPerCta + warp;
+    // one group of GW lanes per game instance (GW = 16: two instances share a warp)
+    const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
+    const int env = blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
     if (env >= p.n_envs) return;
-    Ctx<CELLS> w;
-    ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);                // [record | scratch]
+    Ctx<CELLS, GW> w;
+    ctx_bind(w, td_smem + (size_t)group * p.smem_per_warp, p);               // [record | scratch] per instance
     uint8_t *rec = p.records + (size_t)env * w.record_bytes();
     const td_step_io &io = p.io;
     const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
                                  !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
     // the record and the inputs are requested together: one round trip
     issue_env_load(w, rec);
-    long long in_def = 0, atk_mine = TD_NTYPES;
+    long long in_def = 0;
+    long long atk_mine[TD_ROADS] = {TD_NTYPES, TD_NTYPES, TD_NTYPES};      // lanes 0..7 hold road i's cluster slots
     int in_opp = 0xff;
     if (KIND != TD_KIND_ATK && !MULTI) in_def = io.def_action_dev[env];
-    if (KIND != TD_KIND_DEF && lane < TD_ROADS * TD_CLUSTER)
-        atk_mine = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane];
+    if (KIND != TD_KIND_DEF && lane < TD_CLUSTER) {
+#pragma unroll
+        for (int i = 0; i < TD_ROADS; ++i)
+            atk_mine[i] = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + i * TD_CLUSTER + lane];
+    }
     if (KIND == TD_KIND_DEF && io.opponent_dev != nullptr) in_opp = io.opponent_dev[env];
-    w.ecap = 32 * NCHUNK;
+    w.ecap = GW * NCHUNK;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
+    gsync(w);
     finish_env_load(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
     bool dirty = false;
 
@@ -1193,14 +1233,16 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     auto attacker = [&]() {
         if (w.atk_cd == 0) {
             const int nr = w.mh()->num_roads;
-            for (int i = 0; i < nr; ++i) {
+#pragma unroll
+            for (int i = 0; i < TD_ROADS; ++i) {
+                if (i >= nr) break;
                 if (!(KIND == TD_KIND_2P && MULTI)) {
-                    bool skip = __all_sync(kFull, (lane < i * 8 || lane >= i * 8 + 8) || atk_mine == TD_NTYPES);
+                    bool skip = gall(w, lane >= TD_CLUSTER || atk_mine[i] == TD_NTYPES);
                     if (skip) { fail_atk[n_fail_atk++] = 0; continue; }     // TDAttack.py:39-41
                 }
-                long long before = atk_mine;
-                bool res = summon_cluster(w, i, atk_mine, i * 8);
-                if (KIND == TD_KIND_2P) { atk_mine = before; w.atk_cd = cc.atk_interval; }   // tuple truthiness
+                long long before = atk_mine[i];
+                bool res = summon_cluster(w, i, atk_mine[i], 0);
+                if (KIND == TD_KIND_2P) { atk_mine[i] = before; w.atk_cd = cc.atk_interval; }   // tuple truthiness
                 else if (res) w.atk_cd = cc.atk_interval;
                 fail_atk[n_fail_atk++] = w.fail;
             }
@@ -1224,7 +1266,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         attacker();
         defender();
     }
-    __syncwarp();
+    gsync(w);
 
     int kills, leaks;
     double reward = board_step<NCHUNK>(w, kills, leaks);
@@ -1264,10 +1306,13 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         }
         if (w.flags) p.stats[env].flags |= (uint32_t)w.flags;
     }
-    if (KIND != TD_KIND_DEF && io.real_atk_dev && lane < TD_ROADS * TD_CLUSTER)
-        io.real_atk_dev[(size_t)env * TD_ROADS * TD_CLUSTER + lane] = atk_mine;
+    if (KIND != TD_KIND_DEF && io.real_atk_dev && lane < TD_CLUSTER) {
+#pragma unroll
+        for (int i = 0; i < TD_ROADS; ++i)
+            io.real_atk_dev[(size_t)env * TD_ROADS * TD_CLUSTER + i * TD_CLUSTER + lane] = atk_mine[i];
+    }
     (void)def_ok;
-    __syncwarp();
+    gsync(w);
 
     if (done && io.auto_reset) {
         int next = (w.hdr()->map_id + p.map_stride) % p.n_maps;
@@ -1283,7 +1328,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         if (lane < w.cn) asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word) : "l"(w.mt + w.mt_pos + lane) : "memory");
     }
     if (io.obs_dev) write_obs(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
-    __syncwarp();
+    gsync(w);
     if (w.mt != nullptr && lane < kRngCache) const_cast<uint32_t *>(w.rng_cache())[lane] = next_word;
     store_env(w, p, rec, dirty);
 }
@@ -1296,17 +1341,17 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
     if (mask && !mask[env]) return;
-    Ctx<0> w;
+    Ctx<0, 32> w;
     ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     uint8_t *rec = p.records + (size_t)env * p.record_bytes;
     if (w.lane < (kHdrBytes >> 4)) reinterpret_cast<int4 *>(w.hdr())[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
-    __syncwarp();
+    gsync(w);
     pull_header(w);
     int id = map_ids ? map_ids[env] : env % p.n_maps;
     id = ((id % p.n_maps) + p.n_maps) % p.n_maps;
     reset_env(w, p, id, true);
     if (obs) write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells());
-    __syncwarp();
+    gsync(w);
     store_env(w, p, rec, true);
 }
 
@@ -1316,7 +1361,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const Ste
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;
     if (env >= p.n_envs) return;
-    Ctx<CELLS> w;
+    Ctx<CELLS, 32> w;
     ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     load_env(w, p, p.records + (size_t)env * p.record_bytes);
     write_obs(w, obs + (size_t)env * TD_NCHANNELS * w.ncells());
