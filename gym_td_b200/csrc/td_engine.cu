@@ -18,7 +18,7 @@ struct td_handle {
     int device, kind, L, cells, cells_pad, n_envs;
     int n_maps, map_stride, difficulty;
     int record_bytes, map_bytes, smem_per_warp, scratch_off;
-    int off_static, off_towers, off_enemies;
+    int off_static, off_towers, off_enemies, off_map6, rng_cache_words;
     uint8_t *records;
     uint8_t *maps;
     uint32_t *mt;
@@ -182,6 +182,7 @@ static void fill_params(const td_handle *h, StepParams &p)
     p.off_static = h->off_static;
     p.off_towers = h->off_towers;
     p.off_enemies = h->off_enemies;
+    p.rng_cache_words = h->rng_cache_words;
     p.difficulty = h->difficulty;
     p.opponent_seeded = h->opponent_seeded ? 1 : 0;
 }
@@ -249,7 +250,9 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->cells_pad = round16(h->cells); h->n_envs = n_envs;
     h->n_maps = 0; h->map_stride = n_envs; h->difficulty = 1;
     h->map_bytes = kMapHdrBytes + 2 * h->cells_pad;
-    h->off_static = kOffMap6 + h->cells_pad;
+    h->rng_cache_words = env_kind == TD_KIND_ATK ? kRngCacheAtk : kRngCacheDef;
+    h->off_map6 = kOffRngCache + 4 * h->rng_cache_words;
+    h->off_static = h->off_map6 + h->cells_pad;
     h->off_towers = h->off_static + h->map_bytes;
     h->off_enemies = h->off_towers + TD_CAP_TOWERS * kTowerBytes;
     h->record_bytes = h->off_enemies + TD_CAP_ENEMIES * kEnemyBytes;
@@ -320,7 +323,7 @@ extern "C" int td_get_layout(const td_handle *h, td_layout *out)
     out->off_header = 0;
     out->off_towers = h->off_towers;
     out->off_enemies = h->off_enemies;
-    out->off_map6 = kOffMap6;
+    out->off_map6 = h->off_map6;
     out->tower_stride = kTowerBytes;
     out->enemy_stride = kEnemyBytes;
     out->cap_towers = TD_CAP_TOWERS;

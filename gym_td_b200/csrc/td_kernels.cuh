@@ -48,12 +48,11 @@ constexpr unsigned kFull = 0xffffffffu;
 //     towers 32 x 16 | enemies 64 x 24 ]
 // Everything a step normally needs sits in two contiguous prefixes, fetched in ONE round trip: the first
 // runs from the header to tower kSpecTowers, the second covers enemies [0, kSpecEnemies).
-constexpr int kHdrBytes = 128;            // td_env_header + kRngCache cached generator words
-constexpr int kRngCache = 16;
-constexpr int kOffRngCache = 64;
+constexpr int kOffRngCache = 64;          // td_env_header, then the cached generator words, then map6
+constexpr int kRngCacheDef = 16;          // words cached per env: the defender env's attacker draws ~4 per step,
+constexpr int kRngCacheAtk = 64;          // the attacker env's scripted defender up to ~60 (shuffle of the road cells)
 constexpr int kTowerBytes = 16;
 constexpr int kEnemyBytes = 24;
-constexpr int kOffMap6 = kHdrBytes;
 constexpr int kMapHdrBytes = 16;
 constexpr int kMtWords = 624;
 constexpr int kSpecTowers = 16;           // speculatively staged list prefixes
@@ -98,7 +97,7 @@ struct StepParams {
     EnvStats *stats;           // [n]
     int n_envs, n_maps, map_stride;
     int L, cells, cells_pad, record_bytes, map_bytes, smem_per_warp, scratch_off;
-    int off_static, off_towers, off_enemies;
+    int off_static, off_towers, off_enemies, rng_cache_words;
     int difficulty;
     int opponent_seeded;
     td_step_io io;
@@ -111,7 +110,7 @@ struct StepParams {
 // CELLS == 0: layout read from the kernel parameters (constant bank).
 // GW = lanes per game instance: 32 (one warp per env) or 16 (two envs per warp: the uniform bookkeeping
 // of both is issued once, and twice as many envs are in flight per SM at the same warp count).
-template <int CELLS, int GW>
+template <int CELLS, int GW, int RC = 0>
 struct Ctx {
     static constexpr int kCells = CELLS;
     static constexpr int G = GW;
@@ -136,13 +135,16 @@ struct Ctx {
     __device__ __forceinline__ int ncells() const { return CELLS ? CELLS : pp->cells; }
     __device__ __forceinline__ int cells_pad() const { return CELLS ? kPad : pp->cells_pad; }
     __device__ __forceinline__ int map_bytes() const { return kMapHdrBytes + 2 * cells_pad(); }
-    __device__ __forceinline__ int off_static() const { return kOffMap6 + cells_pad(); }
+    // RC > 0: cached generator words known at compile time; RC == 0: read from the kernel parameters
+    __device__ __forceinline__ int rng_words() const { return RC ? RC : pp->rng_cache_words; }
+    __device__ __forceinline__ int hdr_bytes() const { return kOffRngCache + 4 * rng_words(); }
+    __device__ __forceinline__ int off_static() const { return hdr_bytes() + cells_pad(); }
     __device__ __forceinline__ int off_towers() const { return off_static() + map_bytes(); }
     __device__ __forceinline__ int off_enemies() const { return off_towers() + TD_CAP_TOWERS * kTowerBytes; }
     __device__ __forceinline__ int record_bytes() const { return off_enemies() + TD_CAP_ENEMIES * kEnemyBytes; }
     __device__ __forceinline__ td_env_header *hdr() const { return reinterpret_cast<td_env_header *>(slice); }
     __device__ __forceinline__ const uint32_t *rng_cache() const { return reinterpret_cast<const uint32_t *>(slice + kOffRngCache); }
-    __device__ __forceinline__ uint8_t *map6() const { return slice + kOffMap6; }
+    __device__ __forceinline__ uint8_t *map6() const { return slice + hdr_bytes(); }
     __device__ __forceinline__ MapHdr *mh() const { return reinterpret_cast<MapHdr *>(slice + off_static()); }
     __device__ __forceinline__ uint8_t *cells() const { return slice + off_static() + kMapHdrBytes; }
     __device__ __forceinline__ uint8_t *dist() const { return slice + off_static() + kMapHdrBytes + cells_pad(); }
@@ -354,7 +356,7 @@ __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *re
 {
     push_header(w);
     gsync(w);
-    const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : kHdrBytes);
+    const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : w.hdr_bytes());
     warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
     warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane, W::G);
     warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane, W::G);
@@ -395,9 +397,9 @@ __device__ __forceinline__ void reset_env(W &w, const StepParams &p, int map_id,
 template <class W>
 __device__ __forceinline__ int py_randbelow(W &w, int n)
 {
-    int shift = __clz(n);            // 32 - bit_length(n)
-    uint32_t r = mt_next(w) >> shift;
-    while (r >= (uint32_t)n) r = mt_next(w) >> shift;
+    const int shift = __clz(n);      // 32 - bit_length(n)
+    uint32_t r;
+    do { r = mt_next(w) >> shift; } while (r >= (uint32_t)n);
     return (int)r;
 }
 
@@ -411,18 +413,26 @@ __device__ __forceinline__ double py_random(W &w)
 // ------------------------------------------------------------------------------------------------
 // (a) defender operations -- all arguments and results are warp-uniform
 
-template <class W>
-__device__ __forceinline__ void diamond_add(W &w, int loc, int delta)
+// map[6] += delta on the Manhattan diamond around `loc` (TDBoard.py:239-245, 281-287).  Out of line: it is
+// reached from several build / destruct sites and only on the rare successful operation.
+__device__ __noinline__ void diamond_add_cells(uint8_t *map6, int loc, int delta, int L, int lane, int stride,
+                                               unsigned gmask)
 {
-    const int L = w.L(), D = cc.tower_distance, WD = 2 * D + 1;
+    const int D = cc.tower_distance, WD = 2 * D + 1;
     const int r0 = loc / L, c0 = loc - r0 * L;
-    for (int k = w.lane; k < WD * WD; k += W::G) {
+    for (int k = lane; k < WD * WD; k += stride) {
         int i = k / WD - D, j = k % WD - D;
         int r = r0 + i, c = c0 + j;
         if (abs(i) + abs(j) <= D && r >= 0 && r < L && c >= 0 && c < L)
-            w.map6()[r * L + c] = (uint8_t)(w.map6()[r * L + c] + delta);
+            map6[r * L + c] = (uint8_t)(map6[r * L + c] + delta);
     }
-    gsync(w);
+    __syncwarp(gmask);
+}
+
+template <class W>
+__device__ __forceinline__ void diamond_add(W &w, int loc, int delta)
+{
+    diamond_add_cells(w.map6(), loc, delta, w.L(), w.lane, W::G, w.gmask);
 }
 
 template <class W>
@@ -1188,7 +1198,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
     const int env = blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
     if (env >= p.n_envs) return;
-    Ctx<CELLS, GW> w;
+    constexpr int RC = KIND == TD_KIND_ATK ? kRngCacheAtk : kRngCacheDef;
+    Ctx<CELLS, GW, RC> w;
     ctx_bind(w, td_smem + (size_t)group * p.smem_per_warp, p);               // [record | scratch] per instance
     uint8_t *rec = p.records + (size_t)env * w.record_bytes();
     const td_step_io &io = p.io;
@@ -1321,15 +1332,25 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         dirty = true;
     }
     // Generator words for the next step: requested now, parked in the record after the observation went out.
-    uint32_t next_word = 0;
+    constexpr int kRefill = (RC + GW - 1) / GW;
+    uint32_t next_word[kRefill];
+#pragma unroll
+    for (int q = 0; q < kRefill; ++q) next_word[q] = 0;
     if (w.mt != nullptr) {
         w.ck = 0;
-        w.cn = min(kRngCache, max(kMtWords - w.mt_pos, 0));
-        if (lane < w.cn) asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word) : "l"(w.mt + w.mt_pos + lane) : "memory");
+        w.cn = min(w.rng_words(), max(kMtWords - w.mt_pos, 0));
+#pragma unroll
+        for (int q = 0; q < kRefill; ++q)
+            if (lane + GW * q < w.cn)
+                asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word[q]) : "l"(w.mt + w.mt_pos + lane + GW * q) : "memory");
     }
     if (io.obs_dev) write_obs(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
     gsync(w);
-    if (w.mt != nullptr && lane < kRngCache) const_cast<uint32_t *>(w.rng_cache())[lane] = next_word;
+    if (w.mt != nullptr) {
+#pragma unroll
+        for (int q = 0; q < kRefill; ++q)
+            if (lane + GW * q < RC) const_cast<uint32_t *>(w.rng_cache())[lane + GW * q] = next_word[q];
+    }
     store_env(w, p, rec, dirty);
 }
 
@@ -1344,7 +1365,7 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
     Ctx<0, 32> w;
     ctx_bind(w, td_smem + (size_t)warp * p.smem_per_warp, p);
     uint8_t *rec = p.records + (size_t)env * p.record_bytes;
-    if (w.lane < (kHdrBytes >> 4)) reinterpret_cast<int4 *>(w.hdr())[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
+    if (w.lane < (w.hdr_bytes() >> 4)) reinterpret_cast<int4 *>(w.hdr())[w.lane] = reinterpret_cast<const int4 *>(rec)[w.lane];
     gsync(w);
     pull_header(w);
     int id = map_ids ? map_ids[env] : env % p.n_maps;
