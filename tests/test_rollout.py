@@ -106,3 +106,16 @@ def test_rollout_buffer_on_live_env_matches_oracle():
     assert np.array_equal(advs.cpu().numpy().view(np.uint32), a_ref.view(np.uint32))
     assert np.array_equal(rets.cpu().numpy().view(np.uint32), r_ref.view(np.uint32))
     env.close()
+
+
+@pytest.mark.gpu
+def test_policy_reads_observation_in_place():
+    """BASELINE.json config 5 in miniature: dict actions sampled on the GPU, obs consumed in place."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for env_id, n in (("TD-2p-large-v0", 256), ("TD-def-small-v0", 1024)):
+        out = subprocess.run([sys.executable, os.path.join(root, "examples", "rollout_feed.py"), "--env", env_id,
+                              "--envs", str(n), "--steps", "40"], capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        assert "env-steps/s" in out.stdout
