@@ -589,18 +589,35 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
         TD_CUDA(h, cudaMemcpyAsync((void *)io->opponent_dev, host->opponent_host, n, cudaMemcpyHostToDevice, s));
     rc = td_step(h, io, stream);
     if (rc != TD_OK) return rc;
-#define TD_D2H(dst, src, bytes) \
-    if ((dst) && (src)) TD_CUDA(h, cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s))
-    TD_D2H(host->obs_host, io->obs_dev, n * TD_NCHANNELS * cells * sizeof(float));
-    TD_D2H(host->reward_host, io->reward_dev, n * sizeof(double));
-    TD_D2H(host->done_host, io->done_dev, n);
-    TD_D2H(host->win_host, io->win_dev, n);
-    TD_D2H(host->allow_next_host, io->allow_next_dev, n);
-    TD_D2H(host->real_def_host, io->real_def_dev, def_elems * 8);
-    TD_D2H(host->real_atk_host, io->real_atk_dev, n * TD_ROADS * TD_CLUSTER * 8);
-    TD_D2H(host->fail_def_host, io->fail_def_dev, n * sizeof(int32_t));
-    TD_D2H(host->fail_atk_host, io->fail_atk_dev, n * 4 * sizeof(int32_t));
-#undef TD_D2H
+    // device -> host: outputs that sit at matching offsets of one device slab and one host slab (as TDVecEnv
+    // allocates them) are merged into a single copy; anything else is copied on its own.
+    struct Seg { char *dst; const char *src; size_t bytes; };
+    Seg segs[9];
+    int ns = 0;
+    auto add = [&](void *dst, const void *src, size_t bytes) {
+        if (dst && src && bytes) segs[ns++] = Seg{static_cast<char *>(dst), static_cast<const char *>(src), bytes};
+    };
+    add(host->obs_host, io->obs_dev, n * TD_NCHANNELS * cells * sizeof(float));
+    add(host->reward_host, io->reward_dev, n * sizeof(double));
+    add(host->done_host, io->done_dev, n);
+    add(host->win_host, io->win_dev, n);
+    add(host->allow_next_host, io->allow_next_dev, n);
+    add(host->real_def_host, io->real_def_dev, def_elems * 8);
+    add(host->real_atk_host, io->real_atk_dev, n * TD_ROADS * TD_CLUSTER * 8);
+    add(host->fail_def_host, io->fail_def_dev, n * sizeof(int32_t));
+    add(host->fail_atk_host, io->fail_atk_dev, n * 4 * sizeof(int32_t));
+    std::sort(segs, segs + ns, [](const Seg &x, const Seg &y) { return x.src < y.src; });
+    for (int i = 0; i < ns;) {
+        Seg m = segs[i];
+        int j = i + 1;
+        while (j < ns && segs[j].src >= m.src + m.bytes && segs[j].src - (m.src + m.bytes) <= 256 &&
+               segs[j].src - m.src == segs[j].dst - m.dst) {
+            m.bytes = (size_t)(segs[j].src - m.src) + segs[j].bytes;
+            ++j;
+        }
+        TD_CUDA(h, cudaMemcpyAsync(m.dst, m.src, m.bytes, cudaMemcpyDeviceToHost, s));
+        i = j;
+    }
     TD_CUDA(h, cudaStreamSynchronize(s));
     return TD_OK;
 }

@@ -79,14 +79,28 @@ class TDVecEnv(object):
             self.engine.seed_opponent_python((np.arange(num_envs, dtype=np.uint64) + base).astype(np.uint32))
         N, L, dev = self.num_envs, self.map_size, self.device
         self.obs = torch.empty((N, E.NCH, L, L), dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(N, dtype=torch.float64, device=dev)
-        self._done = torch.zeros(N, dtype=torch.uint8, device=dev)
-        self.win = torch.zeros(N, dtype=torch.int8, device=dev)
-        self._allow = torch.full((N,), 3, dtype=torch.uint8, device=dev)    # AllowNextMove starts True (train/main.py:87)
-        self.fail_def = torch.zeros(N, dtype=torch.int32, device=dev)
-        self.fail_atk = torch.zeros((N, 4), dtype=torch.int32, device=dev)
-        self.real_atk = torch.zeros((N, E.ROADS, E.CLUSTER), dtype=torch.int64, device=dev)
-        self.real_def = torch.zeros((N, 6, L, L) if self.multi_action else (N,), dtype=torch.int64, device=dev)
+        # the small per-step outputs live in one slab (mirrored by one pinned host slab in step_host, so that
+        # td_step_host moves them with a single device->host copy)
+        self._layout, off = {}, 0
+        fields = [("reward", (N,), torch.float64)]
+        if kind != "atk":
+            fields += [("real_def", (N, 6, L, L) if self.multi_action else (N,), torch.int64), ("fail_def", (N,), torch.int32)]
+        if kind != "def":
+            fields += [("real_atk", (N, E.ROADS, E.CLUSTER), torch.int64), ("fail_atk", (N, 4), torch.int32)]
+        fields += [("done", (N,), torch.uint8), ("win", (N,), torch.int8), ("allow", (N,), torch.uint8)]
+        for name, shape, dtype in fields:
+            nbytes = int(np.prod(shape)) * torch.empty((), dtype=dtype).element_size()
+            self._layout[name] = (off, nbytes, shape, dtype)
+            off += (nbytes + 255) & ~255
+        self._slab = torch.zeros(off, dtype=torch.uint8, device=dev)
+        view = lambda slab, k: slab[self._layout[k][0]:self._layout[k][0] + self._layout[k][1]].view(
+            self._layout[k][3]).view(self._layout[k][2])
+        self._view = view
+        opt = lambda k: view(self._slab, k) if k in self._layout else None
+        self.reward, self.real_def, self.real_atk = view(self._slab, "reward"), opt("real_def"), opt("real_atk")
+        self.fail_atk, self.fail_def = opt("fail_atk"), opt("fail_def")
+        self._done, self.win, self._allow = view(self._slab, "done"), view(self._slab, "win"), view(self._slab, "allow")
+        self._allow.fill_(3)                                                 # AllowNextMove starts True (train/main.py:87)
         self._host = None
 
     # -- spaces-like metadata -------------------------------------------------------------------
@@ -151,13 +165,12 @@ class TDVecEnv(object):
     # -- host-buffer path (what a numpy-facing gym caller uses) ------------------------------------
     def _host_buffers(self):
         if self._host is None:
-            N = self.num_envs
-            pin = lambda t: torch.empty(t.shape, dtype=t.dtype).pin_memory()
-            h = dict(reward=pin(self.reward), done=pin(self._done), win=pin(self.win), allow=pin(self._allow),
-                     fail_def=pin(self.fail_def), fail_atk=pin(self.fail_atk), real_atk=pin(self.real_atk),
-                     real_def=pin(self.real_def), obs=None)
-            h["def_dev"] = torch.zeros_like(self.real_def)
-            h["atk_dev"] = torch.zeros_like(self.real_atk)
+            slab = torch.empty(self._slab.shape, dtype=torch.uint8).pin_memory()
+            v = lambda k: self._view(slab, k) if k in self._layout else None
+            h = dict(reward=v("reward"), done=v("done"), win=v("win"), allow=v("allow"), fail_def=v("fail_def"),
+                     fail_atk=v("fail_atk"), real_atk=v("real_atk"), real_def=v("real_def"), obs=None, slab=slab)
+            h["def_dev"] = torch.zeros_like(self.real_def) if self.real_def is not None else None
+            h["atk_dev"] = torch.zeros_like(self.real_atk) if self.real_atk is not None else None
             self._host = h
         return self._host
 
