@@ -224,5 +224,31 @@ class TDVecEnv(object):
         from . import dist
         return dist.reduce_stats(self.stats(), self.device)
 
+    # -- checkpoint / resume (the reference has no env-state checkpoint) ------------------
+    def state_dict(self):
+        """Everything needed to continue bit-identically: env records, opponent generators, last AllowNextMove bits.
+        (The map pool and config are construction arguments and are not part of the snapshot.)"""
+        torch.cuda.synchronize(self.device)
+        d = {"kind": self.kind, "map_size": self.map_size, "num_envs": self.num_envs,
+             "records": torch.from_numpy(self.engine.get_state_raw()), "allow": self._allow.cpu().clone()}
+        try:
+            d["opponent"] = torch.from_numpy(self.engine.get_opponent().astype(np.int64))
+        except E.TdError:
+            d["opponent"] = None
+        return d
+
+    def load_state_dict(self, d):
+        if (d["kind"], d["map_size"], d["num_envs"]) != (self.kind, self.map_size, self.num_envs):
+            raise ValueError("snapshot is for a different env batch")
+        torch.cuda.synchronize(self.device)
+        self.engine.set_state_raw(d["records"].numpy())
+        if d.get("opponent") is not None:
+            # seed_opponent resets the cached-word count of every record, which is what a restore needs:
+            # the cached words are re-read from the restored generator state on the first draw
+            self.engine.seed_opponent(d["opponent"].numpy().astype(np.uint32))
+        self._allow.copy_(d["allow"].to(self.device))
+        self.engine.observe(self.obs, torch.cuda.current_stream(self.device).cuda_stream)
+        return self.obs
+
     def close(self):
         self.engine.close()

@@ -280,3 +280,32 @@ def test_full_size_determinism_and_replayed_subset():
                 oenv = PU.oracle_env_from_map(maps[mid], ocfg)
                 oenv.e.pyrand = py
             assert np.array_equal(sub1[k][0][i].view(np.uint32), oenv.get_states().view(np.uint32)), (i, k)
+
+
+@pytest.mark.parametrize("kind", ["def", "atk"])
+def test_checkpoint_resume_is_bit_identical(kind):
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    N, L = 64, 10
+    env = TDVecEnv(kind, L, N, seed=77, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    def act():
+        return (torch.randint(0, 601, (N,), device="cuda", generator=g) if kind == "def"
+                else torch.randint(0, 5, (N, 3, 8), device="cuda", generator=g))
+    for _ in range(150):
+        env.step(act())
+    snap = env.state_dict()
+    acts = [act() for _ in range(200)]
+    def run():
+        out = []
+        for a in acts:
+            obs, rew, done, info = env.step(a)
+            out.append((obs.view(torch.int32).sum(dtype=torch.int64).item(), rew.clone(), done.clone()))
+        return out
+    first = run()
+    obs0 = env.load_state_dict(snap)
+    second = run()
+    for (s1, r1, d1), (s2, r2, d2) in zip(first, second):
+        assert s1 == s2 and torch.equal(r1.view(torch.int64), r2.view(torch.int64)) and torch.equal(d1, d2)
+    env.close()
