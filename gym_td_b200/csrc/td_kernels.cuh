@@ -35,6 +35,14 @@
 #else
 #define TD_ST(p, v) __stwt((p), (v))
 #endif
+// Debug build (-DTD_DEBUG_BOUNDS): index invariants are checked on the device and a violation sets the sticky
+// flag bit 2 of the env, which TDVecEnv.stats() / the parity tests surface.  (compute-sanitizer is closed on
+// the B200 pool, so this is the memory-safety net next to the bit-exact parity runs.)
+#ifdef TD_DEBUG_BOUNDS
+#define TD_CHECK(w, cond) do { if (!(cond)) (w).flags |= 4; } while (0)
+#else
+#define TD_CHECK(w, cond) do { } while (0)
+#endif
 #ifndef TD_WARPS_PER_CTA
 #define TD_WARPS_PER_CTA 4
 #endif
@@ -442,6 +450,7 @@ __device__ __forceinline__ bool tower_build(W &w, int t, int loc, bool &map6_dir
     if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
     if (w.map6()[loc] > 0) { w.fail = TD_FC_INVALID_POSITION; return false; }
     if (w.nt >= TD_CAP_TOWERS) { w.flags |= 2; w.fail = TD_FC_INVALID_POSITION; return false; }
+    TD_CHECK(w, loc >= 0 && loc < w.ncells() && t >= 0 && t < TD_NTYPES);
     if (w.lane == 0) {
         td_tower_rec &r = w.tw()[w.nt];
         r.cd = 0.0;
@@ -755,6 +764,7 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
             int c = base + w.lane;
             bool on = c < w.ncells() && (w.cells()[c] & 1);
             unsigned b = gballot(w, on);
+            TD_CHECK(w, 2 * (n + __popc(b)) <= max(768, w.cells_pad()));
             if (on) list[n + __popc(b & ((1u << w.lane) - 1u))] = (uint16_t)c;
             n += __popc(b);
         }
@@ -842,6 +852,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
 #pragma unroll
         for (int k = 0; k < NCHUNK; ++k)
             if (E[k].valid) {
+                TD_CHECK(w, rank[k] >= 0 && rank[k] < ne);
                 td_enemy_rec &x = w.en()[rank[k]];
                 x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
                 x.slowdown = (uint8_t)E[k].slow;
@@ -960,6 +971,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
                 E[k].margin = __dsub_rn(E[k].margin, 1.0);
                 int d = (w.cells()[E[k].loc] >> 4) & 3;
                 E[k].loc += (d == 0) ? 1 : (d == 1) ? -1 : (d == 2) ? L : -L;
+                TD_CHECK(w, E[k].loc >= 0 && E[k].loc < w.ncells() && (w.cells()[E[k].loc] & 1));
                 if (E[k].loc == end) { leaked = true; break; }
             }
         }
@@ -973,6 +985,7 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
 #pragma unroll
     for (int k = 0; k < NCHUNK; ++k)
         if (keep[k]) {
+            TD_CHECK(w, newidx[k] >= 0 && newidx[k] < w.ecap);
             td_enemy_rec &x = w.en()[newidx[k]];
             x.LP = E[k].LP; x.margin = E[k].margin; x.loc = (uint16_t)E[k].loc; x.type_lv = (uint8_t)E[k].tl;
             x.slowdown = (uint8_t)E[k].slow;
@@ -1161,6 +1174,7 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
     }
     for (int e = lane; e < ne; e += W::G) {
         const int loc = w.en()[e].loc, ty = w.en()[e].type_lv & 3;
+        TD_CHECK(w, loc < cells && ne <= w.ecap);
         float mn = 1.f, mx = 0.f, sum = 0.f, cnt = 0.f;
         bool leader = true;
         for (int j = 0; j < ne; ++j) {
