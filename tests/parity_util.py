@@ -16,6 +16,9 @@ from gym_td_b200 import mapgen
 from oracle import td_oracle as TO
 
 
+LAST_MAX = {"towers": 0, "enemies": 0}      # longest lists seen by the last run_parity (coverage evidence)
+
+
 def oracle_config_from_engine(cfg):
     """TdConfig (product) -> oracle Config; the two structs have the same field names."""
     o = TO.Config()
@@ -144,6 +147,7 @@ def run_parity(kind, L, n_envs, steps, seed=0, multi=False, opponent="device", d
     """
     import torch
     dev = torch.device("cuda", device)
+    LAST_MAX.update(towers=0, enemies=0)
     rs = np.random.RandomState(seed)
     cfg = make_config(**(cfg_overrides or {}))
     ocfg = oracle_config_from_engine(cfg)
@@ -265,6 +269,8 @@ def run_parity(kind, L, n_envs, steps, seed=0, multi=False, opponent="device", d
             if recs is not None:
                 compare_state(tag, eng, recs[i], o)
             compared += 1
+            LAST_MAX["towers"] = max(LAST_MAX["towers"], o.e.n_towers)
+            LAST_MAX["enemies"] = max(LAST_MAX["enemies"], o.e.n_enemies)
             if out.done:
                 alive[i] = False
         if not alive.any():

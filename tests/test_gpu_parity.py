@@ -59,3 +59,17 @@ def test_config_overrides():
 
 def test_odd_map_size_scalar_store_path():
     assert PU.run_parity("def", 15, n_envs=16, steps=400, seed=31) > 1000
+
+
+def test_dense_boards_exercise_long_lists():
+    """Cheap towers and cheap slow enemies: tower lists beyond the 16 staged speculatively (up to ~30 of the 32
+    slots), enemy lists into the second 32-lane chunk at L=20, many enemies per cell -- the rarely taken
+    multi-pass paths, kept just below the capacities (run_parity asserts that no overflow was flagged)."""
+    ov = dict(tower_cost=[[5, 5]] * 4, defender_init_cost=100, enemy_cost=[[4, 4]] * 4, attacker_init_cost=100,
+              enemy_speed=[[.05, .05], [.04, .04], [.03, .03], [.03, .03]], base_LP=None)
+    assert PU.run_parity("2p", 20, n_envs=12, steps=150, seed=41, opponent="none", cfg_overrides=ov) > 1000
+    assert PU.LAST_MAX["towers"] > 16 and PU.LAST_MAX["enemies"] > 32, PU.LAST_MAX
+    assert PU.run_parity("atk", 20, n_envs=8, steps=150, seed=43, opponent="device", difficulty=2, cfg_overrides=ov) > 800
+    ov10 = dict(ov, enemy_cost=[[7, 7]] * 4)
+    assert PU.run_parity("def", 10, n_envs=12, steps=150, seed=42, opponent="device", cfg_overrides=ov10) > 1000
+    assert PU.LAST_MAX["towers"] > 16 and PU.LAST_MAX["enemies"] > 16, PU.LAST_MAX
