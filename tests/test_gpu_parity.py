@@ -73,3 +73,10 @@ def test_dense_boards_exercise_long_lists():
     ov10 = dict(ov, enemy_cost=[[7, 7]] * 4)
     assert PU.run_parity("def", 10, n_envs=12, steps=150, seed=42, opponent="device", cfg_overrides=ov10) > 1000
     assert PU.LAST_MAX["towers"] > 16 and PU.LAST_MAX["enemies"] > 16, PU.LAST_MAX
+
+
+@pytest.mark.parametrize("L,n", [(8, 1), (13, 3), (25, 5), (40, 7), (64, 2)])
+def test_unusual_board_sizes_and_batch_sizes(L, n):
+    """The run-time-size kernel variant ('TD-def-v0' with a map_size kwarg), batches that do not fill a CTA."""
+    assert PU.run_parity("def", L, n_envs=n, steps=250, seed=50 + L, opponent="device") > 100
+    assert PU.run_parity("2p", L, n_envs=n, steps=120, seed=60 + L, opponent="none", multi=True) > 50
