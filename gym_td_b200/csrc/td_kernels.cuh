@@ -104,6 +104,7 @@ struct StepParams {
     uint32_t *mt;              // [n][624] scripted-opponent generator words (may be NULL)
     EnvStats *stats;           // [n]
     int n_envs, n_maps, map_stride;
+    int env_begin;             // the step kernel covers envs [env_begin, n_envs) (chunked host-path launches)
     int L, cells, cells_pad, record_bytes, map_bytes, smem_per_warp, scratch_off;
     int off_static, off_towers, off_enemies, rng_cache_words;
     int difficulty;
@@ -1210,7 +1211,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
-    const int env = blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
+    const int env = p.env_begin + blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
     if (env >= p.n_envs) return;
     constexpr int RC = KIND == TD_KIND_ATK ? kRngCacheAtk : kRngCacheDef;
     Ctx<CELLS, GW, RC> w;

@@ -102,6 +102,8 @@ class TDVecEnv(object):
         self._done, self.win, self._allow = view(self._slab, "done"), view(self._slab, "win"), view(self._slab, "allow")
         self._allow.fill_(3)                                                 # AllowNextMove starts True (train/main.py:87)
         self._host = None
+        self._io_cache = None
+        self._hio_cache = None
 
     # -- spaces-like metadata -------------------------------------------------------------------
     @property
@@ -134,10 +136,19 @@ class TDVecEnv(object):
         return action["Defender"], action["Attacker"]
 
     def _io(self, d, a, opponent=None):
-        return E.Engine.make_io(def_action=d, atk_action=a, opponent=opponent, multi_action=self.multi_action,
-                                auto_reset=self.auto_reset, obs=self.obs, reward=self.reward, done=self._done,
-                                win=self.win, allow_next=self._allow, real_def=self.real_def,
-                                real_atk=self.real_atk, fail_def=self.fail_def, fail_atk=self.fail_atk)
+        """The td_step_io of this env: output pointers are fixed, only the action pointers change per call."""
+        io = self._io_cache
+        if io is None:
+            io = self._io_cache = E.Engine.make_io(
+                multi_action=self.multi_action, auto_reset=self.auto_reset, obs=self.obs, reward=self.reward,
+                done=self._done, win=self.win, allow_next=self._allow, real_def=self.real_def,
+                real_atk=self.real_atk, fail_def=self.fail_def, fail_atk=self.fail_atk)
+        io.auto_reset = int(self.auto_reset)
+        io.obs_dev = E._ptr(self.obs)
+        io.def_action_dev = d.data_ptr() if d is not None else None
+        io.atk_action_dev = a.data_ptr() if a is not None else None
+        io.opponent_dev = opponent.data_ptr() if opponent is not None else None
+        return io
 
     def _check(self, d, a):
         N, L = self.num_envs, self.map_size
@@ -182,16 +193,18 @@ class TDVecEnv(object):
         if want_obs and h["obs"] is None:
             h["obs"] = torch.empty(self.obs.shape, dtype=torch.float32).pin_memory()
         io = self._io(h["def_dev"] if d is not None else None, h["atk_dev"] if a is not None else None)
-        hio = E.TdHostIO()
+        hio = self._hio_cache
+        if hio is None:
+            hio = self._hio_cache = E.TdHostIO()
+            hio.reward_host, hio.done_host, hio.win_host = h["reward"].data_ptr(), h["done"].data_ptr(), h["win"].data_ptr()
+            hio.allow_next_host = h["allow"].data_ptr()
+            if self.kind != "atk":
+                hio.real_def_host, hio.fail_def_host = h["real_def"].data_ptr(), h["fail_def"].data_ptr()
+            if self.kind != "def":
+                hio.real_atk_host, hio.fail_atk_host = h["real_atk"].data_ptr(), h["fail_atk"].data_ptr()
         hio.def_action_host = d.data_ptr() if d is not None else None
         hio.atk_action_host = a.data_ptr() if a is not None else None
         hio.obs_host = h["obs"].data_ptr() if want_obs else None
-        hio.reward_host, hio.done_host, hio.win_host = h["reward"].data_ptr(), h["done"].data_ptr(), h["win"].data_ptr()
-        hio.allow_next_host = h["allow"].data_ptr()
-        if self.kind != "atk":
-            hio.real_def_host, hio.fail_def_host = h["real_def"].data_ptr(), h["fail_def"].data_ptr()
-        if self.kind != "def":
-            hio.real_atk_host, hio.fail_atk_host = h["real_atk"].data_ptr(), h["fail_atk"].data_ptr()
         self.engine.step_host(io, hio, torch.cuda.current_stream(self.device).cuda_stream)
         return h
 

@@ -309,3 +309,16 @@ def test_checkpoint_resume_is_bit_identical(kind):
     for (s1, r1, d1), (s2, r2, d2) in zip(first, second):
         assert s1 == s2 and torch.equal(r1.view(torch.int64), r2.view(torch.int64)) and torch.equal(d1, d2)
     env.close()
+
+
+@pytest.mark.parametrize("chunks", ["1", "3", "4"])
+def test_chunked_host_path_equals_device_path(chunks):
+    """td_step_host cuts large batches into chunks on two internal streams; results must not depend on it."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TD_HOST_CHUNKS=chunks)
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_chunk_check.py")], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
+    assert "chunked host path ok" in out.stdout
