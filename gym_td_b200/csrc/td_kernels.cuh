@@ -1259,18 +1259,24 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     auto attacker = [&]() {
         if (w.atk_cd == 0) {
             const int nr = w.mh()->num_roads;
-#pragma unroll
-            for (int i = 0; i < TD_ROADS; ++i) {
-                if (i >= nr) break;
-                if (!(KIND == TD_KIND_2P && MULTI)) {
-                    bool skip = gall(w, lane >= TD_CLUSTER || atk_mine[i] == TD_NTYPES);
-                    if (skip) { fail_atk[n_fail_atk++] = 0; continue; }     // TDAttack.py:39-41
+            // one instance of the cluster code for all roads (kept rolled: the kernel is instruction-cache bound)
+#pragma unroll 1
+            for (int i = 0; i < nr; ++i) {
+                long long cur = i == 0 ? atk_mine[0] : (i == 1 ? atk_mine[1] : atk_mine[2]);
+                int code = 0;
+                bool skip = false;
+                if (!(KIND == TD_KIND_2P && MULTI))
+                    skip = gall(w, lane >= TD_CLUSTER || cur == TD_NTYPES);           // TDAttack.py:39-41
+                if (!skip) {
+                    const long long before = cur;
+                    const bool res = summon_cluster(w, i, cur, 0);
+                    if (KIND == TD_KIND_2P) { cur = before; w.atk_cd = cc.atk_interval; }   // tuple truthiness
+                    else if (res) w.atk_cd = cc.atk_interval;
+                    code = w.fail;
+                    if (i == 0) atk_mine[0] = cur; else if (i == 1) atk_mine[1] = cur; else atk_mine[2] = cur;
                 }
-                long long before = atk_mine[i];
-                bool res = summon_cluster(w, i, atk_mine[i], 0);
-                if (KIND == TD_KIND_2P) { atk_mine[i] = before; w.atk_cd = cc.atk_interval; }   // tuple truthiness
-                else if (res) w.atk_cd = cc.atk_interval;
-                fail_atk[n_fail_atk++] = w.fail;
+                if (n_fail_atk == 0) fail_atk[0] = code; else if (n_fail_atk == 1) fail_atk[1] = code; else fail_atk[2] = code;
+                ++n_fail_atk;
             }
             if (KIND == TD_KIND_2P && MULTI) n_fail_atk = 0;
         }
