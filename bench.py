@@ -173,13 +173,35 @@ def run_reference_arm(args):
                 cpu_baseline={"value": value, "unit": UNIT, "cores": cores, "kind": kind_name, "sample": sample},
                 e2e={"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun) write to fd 1; keep it for the ONE JSON line only."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
         return 0
@@ -361,7 +383,7 @@ def main():
             line["cpu_port"] = port
         else:
             line["cpu_baseline"] = port
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
