@@ -587,6 +587,38 @@ extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
 // Host-buffer step.  Large batches are cut into chunks that alternate between two internal streams, so that
 // the host->device copy of chunk c+1 and the device->host copy of chunk c-1 overlap the kernel of chunk c
 // (instances are independent, so a chunk is a complete unit of work).
+extern "C" int td_snapshot(td_handle *h, void *records_out_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (!records_out_dev) return fail(h, TD_E_INVALID, "td_snapshot: records_out_dev is NULL");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    TD_CUDA(h, cudaMemcpyAsync(records_out_dev, h->records, (size_t)h->n_envs * h->record_bytes,
+                               cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TD_OK;
+}
+
+extern "C" int td_observe_snapshot(td_handle *h, const void *records_dev, int n, float *obs_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (!records_dev || !obs_dev || n < 1) return fail(h, TD_E_INVALID, "td_observe_snapshot: bad arguments");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    p.records = static_cast<uint8_t *>(const_cast<void *>(records_dev));     // read-only in the observe kernel
+    p.n_envs = n;
+    const int grid = (n + kWarpsPerCta - 1) / kWarpsPerCta, block = kWarpsPerCta * 32;
+    const size_t smem = smem_of(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (h->L) {
+    case 10: td_observe_kernel<100><<<grid, block, smem, s>>>(p, obs_dev); break;
+    case 20: td_observe_kernel<400><<<grid, block, smem, s>>>(p, obs_dev); break;
+    case 30: td_observe_kernel<900><<<grid, block, smem, s>>>(p, obs_dev); break;
+    default: td_observe_kernel<0><<<grid, block, smem, s>>>(p, obs_dev); break;
+    }
+    TD_CUDA(h, cudaGetLastError());
+    return TD_OK;
+}
+
 extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, void *stream)
 {
     if (!h) return TD_E_INVALID;

@@ -90,7 +90,7 @@ EXPORTS = ["td_abi_version", "td_last_error", "td_default_config", "td_mapgen", 
            "td_destroy", "td_set_config", "td_get_layout", "td_upload_maps", "td_set_map_stride", "td_reset",
            "td_seed_opponent", "td_set_difficulty", "td_step", "td_observe", "td_step_host", "td_get_state",
            "td_set_state", "td_get_opponent", "td_get_stats", "td_reset_stats", "td_rollout_mask", "td_rollout_record",
-           "td_gae"]
+           "td_gae", "td_snapshot", "td_observe_snapshot"]
 
 
 def lib():
@@ -125,6 +125,8 @@ def lib():
         L.td_set_state.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.td_get_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.td_reset_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.td_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.td_observe_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.td_rollout_mask.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.td_rollout_record.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

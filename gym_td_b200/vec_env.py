@@ -237,6 +237,32 @@ class TDVecEnv(object):
         from . import dist
         return dist.reduce_stats(self.stats(), self.device)
 
+    # -- compact observations ----------------------------------------------------------------
+    def snapshot(self, out=None):
+        """Copy the current env records (record_bytes per env, ~2.5 KB at L=10 instead of the 18 KB observation)
+        into `out` ([num_envs, record_bytes] uint8 CUDA tensor, allocated when None).  The observation can be
+        rebuilt from a record at any time with observe_snapshot()."""
+        rb = self.engine.layout.record_bytes
+        if out is None:
+            out = torch.empty((self.num_envs, rb), dtype=torch.uint8, device=self.device)
+        assert out.is_cuda and out.is_contiguous() and out.numel() == self.num_envs * rb
+        eng = self.engine
+        eng._check(eng._lib.td_snapshot(eng._h, out.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
+    def observe_snapshot(self, records, out=None):
+        """(n, 45, L, L) float32 observations of `records` ([n, record_bytes] uint8 CUDA tensor of stored records)."""
+        rb = self.engine.layout.record_bytes
+        records = records.view(-1, rb)
+        n, L = records.shape[0], self.map_size
+        assert records.is_cuda and records.is_contiguous() and records.dtype == torch.uint8
+        if out is None:
+            out = torch.empty((n, E.NCH, L, L), dtype=torch.float32, device=self.device)
+        eng = self.engine
+        eng._check(eng._lib.td_observe_snapshot(eng._h, records.data_ptr(), n, out.data_ptr(),
+                                                torch.cuda.current_stream(self.device).cuda_stream))
+        return out
+
     # -- checkpoint / resume (SURVEY.md section 5: the reference has no env-state checkpoint) ------------------
     def state_dict(self):
         """Everything needed to continue bit-identically: env records, opponent generators, last AllowNextMove bits.

@@ -256,6 +256,15 @@ int td_get_opponent(td_handle *h, int first_env, int n, uint32_t *states_host);
 int td_get_stats(td_handle *h, td_stats *out, void *stream);
 int td_reset_stats(td_handle *h, void *stream);
 
+/* ---- compact observations: an env record (td_layout.record_bytes, ~2.5 KB at L=10) holds
+ * everything the 18 KB float32 observation is a function of, including the static map.  A learner can keep
+ * records instead of observations and rebuild any of them on demand:
+ * td_snapshot          copies the n_envs current records to caller memory ([n_envs, record_bytes] bytes, device)
+ * td_observe_snapshot  builds the (45, L, L) float32 observations of `n` stored records (kernel (f) alone,
+ *                      TDBoard.get_states, gym_TD/envs/TDBoard.py:85-144) */
+int td_snapshot(td_handle *h, void *records_out_dev, void *stream);
+int td_observe_snapshot(td_handle *h, const void *records_dev, int n, float *obs_dev, void *stream);
+
 /* ---- rollout consumer: the per-step bookkeeping of the reference's training loop ----
  * td_rollout_mask    <- train/main.py:130-132       actions of envs that may not move become empty_action()
  * td_rollout_record  <- train/PPO/Callbacks.py:21-23 + train/PPO/Model.py:134-140

@@ -322,3 +322,27 @@ def test_chunked_host_path_equals_device_path(chunks):
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert "chunked host path ok" in out.stdout
+
+
+def test_observations_rebuilt_from_compact_snapshots():
+    """f4: keep 2.5 KB records instead of 18 KB observations, rebuild any observation later, bit-identical."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    N, L, T = 96, 10, 40
+    env = TDVecEnv("def", L, N, seed=5, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    rb = env.engine.layout.record_bytes
+    store = torch.empty((T, N, rb), dtype=torch.uint8, device="cuda")
+    obs_ref = []
+    for t in range(T):
+        obs, _, _, _ = env.step(torch.randint(0, 601, (N,), device="cuda", generator=g))
+        env.snapshot(store[t])
+        obs_ref.append(obs.clone())
+    assert rb * 7 < 45 * L * L * 4
+    picks = torch.tensor([0, 7, 39, 22, 13], device="cuda")
+    rebuilt = env.observe_snapshot(store[picks].contiguous())
+    rebuilt = rebuilt.view(len(picks), N, 45, L, L)
+    for k, t in enumerate(picks.tolist()):
+        assert torch.equal(rebuilt[k].view(torch.int32), obs_ref[t].view(torch.int32)), t
+    env.close()
