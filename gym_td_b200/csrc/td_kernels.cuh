@@ -296,30 +296,33 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// Load the next <= 32 words (untempered) into the lanes; a no-op when the state needs a twist first.
+// One window of tempered words lives in the lanes (lane i holds the i-th next word) and is consumed with a
+// shuffle per draw.  It is refilled first from the words cached in the record (no memory round trip), then from
+// the generator state in HBM (twisting it when exhausted).  `ck` counts cached words moved into a window.
 template <class W>
 __device__ __forceinline__ void mt_fill_window(W &w)
 {
-    int n = kMtWords - w.mt_pos;
-    w.win_n = n < W::G ? (n < 0 ? 0 : n) : W::G;
+    uint32_t y = 0u;
+    if (w.ck < w.cn) {
+        const int n = min(W::G, w.cn - w.ck);
+        if (w.lane < n) y = w.rng_cache()[w.ck + w.lane];
+        w.ck += n;
+        w.win_n = n;
+    } else {
+        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane, W::G, w.gmask); w.mt_pos = 0; }
+        const int n = min(W::G, kMtWords - w.mt_pos);
+        if (w.lane < n) y = w.mt[w.mt_pos + w.lane];
+        w.win_n = n;
+    }
+    w.win = mt_temper(y);
     w.win_k = 0;
-    w.win = w.lane < w.win_n ? w.mt[w.mt_pos + w.lane] : 0u;
 }
 
 template <class W>
 __device__ __forceinline__ uint32_t mt_next(W &w)
 {
-    if (w.ck < w.cn) {                                   // words staged with the record: no extra round trip
-        uint32_t r = mt_temper(w.rng_cache()[w.ck]);
-        ++w.ck;
-        ++w.mt_pos;
-        return r;
-    }
-    if (w.win_k == w.win_n) {
-        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane, W::G, w.gmask); w.mt_pos = 0; }
-        mt_fill_window(w);
-    }
-    uint32_t r = mt_temper(gshfl(w, w.win, w.win_k));
+    if (w.win_k == w.win_n) mt_fill_window(w);
+    const uint32_t r = gshfl(w, w.win, w.win_k);
     ++w.win_k;
     ++w.mt_pos;
     return r;
