@@ -153,6 +153,13 @@ static int upload_config(td_handle *h, const td_config *c)
     d.rate_final = c->attacker_cost_final_rate;
     d.def_rate = c->defender_cost_rate;
     d.upgrade_at = c->enemy_upgrade_at;
+    // progress = steps / max_steps is monotone in steps: the first step count whose f64 quotient reaches the
+    // threshold decides the enemy level exactly like `self.progress >= config.enemy_upgrade_at` does
+    d.upgrade_step = 0x7fffffff;
+    for (int sidx = 0; sidx <= c->max_episode_steps + 1; ++sidx) {
+        volatile double prog = (double)sidx / (double)c->max_episode_steps;
+        if (prog >= c->enemy_upgrade_at) { d.upgrade_step = sidx; break; }
+    }
     d.frozen_time = c->frozen_time;
     d.base_LP = c->base_LP < 0 ? -1 : c->base_LP;
     d.tower_distance = c->tower_distance;

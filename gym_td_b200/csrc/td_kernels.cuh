@@ -81,6 +81,7 @@ struct DevConfig {
     double destruct_return, frozen_ratio, atk_init_cost, def_init_cost, max_cost;
     double reward_kill, penalty_leak, reward_time, rate_init, rate_final, def_rate, upgrade_at;
     int frozen_time, base_LP, tower_distance, atk_interval, def_interval, max_steps;
+    int upgrade_step;       // smallest s with (double)s / max_steps >= enemy_upgrade_at (TDBoard.py:201 without the division)
 };
 
 __constant__ DevConfig cc;
@@ -637,7 +638,7 @@ template <class W>
 __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, int lane_base)
 {
     const int start = w.mh()->start[road];
-    const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
+    const int lv = w.steps >= cc.upgrade_step ? 1 : 0;      // progress >= enemy_upgrade_at
     const int tv = (mine < 0 || mine >= TD_NTYPES) ? TD_NTYPES : (int)mine;     // 4 == enemy_types: empty slot
     const unsigned b0 = gballot(w, tv & 1) >> lane_base, b1 = gballot(w, tv & 2) >> lane_base,
                    b2 = gballot(w, tv & 4) >> lane_base;
@@ -681,7 +682,7 @@ template <class W>
 __device__ __forceinline__ void summon_uniform(W &w, int t, int road)
 {
     const int start = w.mh()->start[road];
-    const int lv = ((double)w.steps / (double)cc.max_steps) >= cc.upgrade_at ? 1 : 0;
+    const int lv = w.steps >= cc.upgrade_step ? 1 : 0;      // progress >= enemy_upgrade_at
     const double cost = cc.enemy_cost[t][lv];
     int n = 0;
 #pragma unroll 1
