@@ -346,3 +346,36 @@ def test_observations_rebuilt_from_compact_snapshots():
     for k, t in enumerate(picks.tolist()):
         assert torch.equal(rebuilt[k].view(torch.int32), obs_ref[t].view(torch.int32)), t
     env.close()
+
+
+def test_param_config_reaches_the_device_like_the_reference():
+    """paramConfig(**kw) before make(): same observable behaviour as the reference with the same config."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference not present on this box")
+    import gym_td_b200 as G
+    from oracle import ref_harness as RH
+    ref_loader.load()
+    np.seterr(all="ignore")
+    kw = dict(base_LP=None, defender_init_cost=45, attacker_init_cost=30, max_cost=80, reward_kill=0.25,
+              tower_destruct_return=0.75, frozen_time=3)
+    old = {k: getattr(G.config, k) for k in kw}
+    G.paramConfig(**kw)
+    try:
+        with RH.ref_config_override(**kw):
+            ref = RH.make_env("2p", 10, 77)
+            mine = G.make("TD-2p-small-v0", seed=77)
+            assert np.array_equal(ref._board.get_states(), mine._board.get_states())
+            rs = np.random.RandomState(8)
+            for t in range(300):
+                a = {"Attacker": rs.randint(0, 5, size=(3, 8)), "Defender": RH.smart_defender_action(ref._board, rs)}
+                o1, r1, d1, i1 = ref.step(a)
+                o2, r2, d2, i2 = mine.step(a)
+                assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32)) and repr(r1) == repr(r2) and d1 == d2, t
+                assert repr(i1["Win"]) == repr(i2["Win"])
+                if d1:
+                    break
+            assert t == 299 or d1          # base_LP=None: only the step limit ends the episode
+            mine.close()
+    finally:
+        G.paramConfig(**old)
