@@ -32,14 +32,15 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     extra = os.environ.get("TD_NVCC_EXTRA", "").split()      # experiments, e.g. -DTD_MIN_BLOCKS=6
-    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + \
+    out = os.environ.get("TD_BUILD_OUT", OUT)                # experiments: a variant library next to the default
+    cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed (%d): %s" % (res.returncode, " ".join(cmd)))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

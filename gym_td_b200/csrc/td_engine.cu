@@ -209,6 +209,17 @@ static size_t smem_of(const td_handle *h) { return (size_t)kWarpsPerCta * h->sme
 
 static int step_group_width(const td_handle *h) { return h->L == 10 ? TD_GROUP_SMALL : 32; }
 
+// Dynamic shared memory of one step CTA.  Boards whose observation is >= 128 KB ask for at least 75 KB so that
+// three CTAs (12 warps = 12 open observation streams) share an SM instead of six: HBM write efficiency falls
+// with the number of long streams written side by side (tools/storebench_sized.cu, test F: 162 KB regions at
+// 4 / 12 / 24 warps per SM -> 7.0 / 6.3 / 5.75 TB/s), and the rules of a large board are a small part of the step.
+static size_t step_smem_bytes(const td_handle *h)
+{
+    size_t bytes = (size_t)(kWarpsPerCta * 32 / step_group_width(h)) * h->smem_per_warp;
+    if ((size_t)TD_NCHANNELS * h->cells * sizeof(float) >= 128 * 1024) bytes = std::max(bytes, (size_t)75 * 1024);
+    return bytes;
+}
+
 static int step_variant(int kind, bool multi)
 {
     return kind == TD_KIND_DEF ? (multi ? 1 : 0) : kind == TD_KIND_ATK ? 2 : (multi ? 4 : 3);
@@ -278,7 +289,7 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     if (rc != TD_OK) return bail(rc);
     if ((e = cudaSetDevice(device)) != cudaSuccess) { h->err = cudaGetErrorString(e); return bail(TD_E_CUDA); }
     size_t smem = smem_of(h);
-    const size_t step_smem = smem * (32 / step_group_width(h));          // instances per CTA x slice
+    const size_t step_smem = step_smem_bytes(h);
     if (step_smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
     if ((e = for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
         (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
@@ -537,7 +548,7 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
     p.n_envs = begin + count;
     const int per_cta = kWarpsPerCta * 32 / step_group_width(h);         // game instances per CTA
     const int grid = (count + per_cta - 1) / per_cta, block = kWarpsPerCta * 32;
-    size_t smem = (size_t)per_cta * h->smem_per_warp;
+    size_t smem = step_smem_bytes(h);
     static const int pad_kb = getenv("TD_STEP_SMEM_KB") ? atoi(getenv("TD_STEP_SMEM_KB")) : 0;   // experiments
     if (pad_kb > 0 && (size_t)pad_kb * 1024 > smem) {
         smem = (size_t)pad_kb * 1024;

@@ -1051,13 +1051,11 @@ __device__ __forceinline__ void store_run(float4 *p, float v, int lane)
 
 // CELLS > 0: compile-time board size (runs of equal planes are unrolled stores with immediate offsets).
 // CELLS == 0: run-time board size, plane by plane (also handles L*L not divisible by 4).
+// Step 1 of the observation: the 12 broadcast plane values, one lane each, parked behind ratio[64] in scratch.
 template <class W>
-__device__ __forceinline__ void write_obs(W &w, float *o)
+__device__ __forceinline__ void obs_prepare(W &w)
 {
-    constexpr int CELLS = W::kCells;
-    const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells();
-    const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-    const float maxd = (float)w.mh()->maxd_p1;
+    const int lane = w.lane;
     // The 12 broadcast values (f64 quotients rounded once to f32, TDBoard.py:115-125,134-142), one per lane:
     // lane 0 -> plane 5, 1 -> 11, 2 -> 12, 3 -> 13, 4..7 -> 41..44 (cost_def / enemy_cost / 8), 8..11 -> 21..24.
     float *pv = reinterpret_cast<float *>(w.scratch()) + 64;         // [48], behind ratio[64]
@@ -1081,16 +1079,29 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
         if (lane < 12) pv[plane] = val;
         gsync(w);
     }
+}
+
+// Step 2: the dense planes of the env whose record sits in w.slice, written by NT cooperating threads
+// (tid in [0, NT)): NT = W::G for one group per env, NT = the CTA size for the CTA-cooperative sweep.
+// Only the slice pointers of `w` are used.
+template <int NT, class W>
+__device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
+{
+    constexpr int CELLS = W::kCells;
+    const int cells = CELLS > 0 ? CELLS : w.ncells();
+    const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+    const float maxd = (float)w.mh()->maxd_p1;
+    const float *pv = reinterpret_cast<const float *>(w.scratch()) + 64;
     if (CELLS > 0 && vec) {
         constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
-        constexpr int kIters = (C4 + W::G - 1) / W::G;
+        constexpr int kIters = (C4 + NT - 1) / NT;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
         const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
         const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
 #pragma unroll
         for (int it = 0; it < kIters; ++it) {
-            const int q = lane + W::G * it;
+            const int q = tid + NT * it;
             if (q < C4) {
                 const uchar4 c = cb[q], d = db[q], m = mb[q];
 #pragma unroll
@@ -1103,52 +1114,52 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
                                                      m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
             }
         }
-        store_run<C4, W::G>(o4 + 4 * C4, 0.f, lane);
-        store_run<C4, W::G>(o4 + 5 * C4, pv[5], lane);
-        store_run<3 * C4, W::G>(o4 + 6 * C4, 0.f, lane);
-        store_run<C4, W::G>(o4 + 10 * C4, 0.f, lane);
+        store_run<C4, NT>(o4 + 4 * C4, 0.f, tid);
+        store_run<C4, NT>(o4 + 5 * C4, pv[5], tid);
+        store_run<3 * C4, NT>(o4 + 6 * C4, 0.f, tid);
+        store_run<C4, NT>(o4 + 10 * C4, 0.f, tid);
 #pragma unroll
-        for (int k = 11; k < 14; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
-        store_run<6 * C4, W::G>(o4 + 15 * C4, 0.f, lane);
+        for (int k = 11; k < 14; ++k) store_run<C4, NT>(o4 + k * C4, pv[k], tid);
+        store_run<6 * C4, NT>(o4 + 15 * C4, 0.f, tid);
 #pragma unroll
-        for (int k = 21; k < 25; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
-        store_run<16 * C4, W::G>(o4 + 25 * C4, 0.f, lane);
+        for (int k = 21; k < 25; ++k) store_run<C4, NT>(o4 + k * C4, pv[k], tid);
+        store_run<16 * C4, NT>(o4 + 25 * C4, 0.f, tid);
 #pragma unroll
-        for (int k = 41; k < 45; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
+        for (int k = 41; k < 45; ++k) store_run<C4, NT>(o4 + k * C4, pv[k], tid);
     } else if (vec) {
         const int c4 = cells >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
         const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
         const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
-        for (int q = lane; q < c4; q += W::G) {
+        for (int q = tid; q < c4; q += NT) {
             uchar4 c = cb[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 TD_ST(o4 + k * c4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
                                                     (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
         }
-        fill_planes(o, 4, 1, cells, 0.f, lane, W::G);
-        fill_planes(o, 5, 1, cells, pv[5], lane, W::G);
-        fill_planes(o, 6, 3, cells, 0.f, lane, W::G);
-        for (int q = lane; q < c4; q += W::G) {
+        fill_planes(o, 4, 1, cells, 0.f, tid, NT);
+        fill_planes(o, 5, 1, cells, pv[5], tid, NT);
+        fill_planes(o, 6, 3, cells, 0.f, tid, NT);
+        for (int q = tid; q < c4; q += NT) {
             uchar4 d = db[q];
             TD_ST(o4 + 9 * c4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
                                                 __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
         }
-        fill_planes(o, 10, 1, cells, 0.f, lane, W::G);
-        for (int k = 11; k < 14; ++k) fill_planes(o, k, 1, cells, pv[k], lane, W::G);
-        for (int q = lane; q < c4; q += W::G) {
+        fill_planes(o, 10, 1, cells, 0.f, tid, NT);
+        for (int k = 11; k < 14; ++k) fill_planes(o, k, 1, cells, pv[k], tid, NT);
+        for (int q = tid; q < c4; q += NT) {
             uchar4 m = mb[q];
             TD_ST(o4 + 14 * c4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
                                                  m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
         }
-        fill_planes(o, 15, 6, cells, 0.f, lane, W::G);
-        for (int k = 21; k < 25; ++k) fill_planes(o, k, 1, cells, pv[k], lane, W::G);
-        fill_planes(o, 25, 16, cells, 0.f, lane, W::G);
-        for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], lane, W::G);
+        fill_planes(o, 15, 6, cells, 0.f, tid, NT);
+        for (int k = 21; k < 25; ++k) fill_planes(o, k, 1, cells, pv[k], tid, NT);
+        fill_planes(o, 25, 16, cells, 0.f, tid, NT);
+        for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], tid, NT);
     } else {
-        for (int q = lane; q < cells; q += W::G) {
+        for (int q = tid; q < cells; q += NT) {
             uint8_t c = w.cells()[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k) TD_ST(o + (size_t)k * cells + q, (float)((c >> k) & 1));
@@ -1156,9 +1167,17 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
             TD_ST(o + (size_t)14 * cells + q, w.map6()[q] == 0 ? 1.f : 0.f);
         }
         for (int k = 4; k < TD_NCHANNELS; ++k)
-            if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], lane, W::G);
+            if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], tid, NT);
     }
+}
 
+// Step 3: the sparse one-hots and enemy statistics, 4-byte stores on top of the dense planes (the caller
+// orders them after every dense store to this env: __syncwarp for one group, __syncthreads for a CTA sweep).
+template <class W>
+__device__ __forceinline__ void obs_sparse(W &w, float *o)
+{
+    constexpr int CELLS = W::kCells;
+    const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells();
     // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
     float *ratio = reinterpret_cast<float *>(w.scratch());       // [64]
     const int ne = w.ne;
@@ -1201,6 +1220,14 @@ __device__ __forceinline__ void write_obs(W &w, float *o)
     }
 }
 
+template <class W>
+__device__ __forceinline__ void write_obs(W &w, float *o)
+{
+    obs_prepare(w);
+    obs_dense<W::G>(w, o, w.lane);
+    obs_sparse(w, o);
+}
+
 // ------------------------------------------------------------------------------------------------
 // kernels
 
@@ -1210,17 +1237,15 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 #define TD_MIN_BLOCKS 6
 #endif
 
-template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const StepParams p)
+// One env's rules for one step: load the record, apply the actions / scripted opponent, advance the board, emit
+// the per-env outputs, auto-reset.  Leaves the updated record in the slice and requests the generator words of
+// the next step (next_word, parked in the record by the caller once the observation went out).
+template <int KIND, bool MULTI, int NCHUNK, class W, int NREFILL>
+__device__ __forceinline__ void env_rules(const StepParams &p, const int env, W &w, uint8_t *rec, bool &dirty,
+                                          uint32_t (&next_word)[NREFILL])
 {
-    // one group of GW lanes per game instance (GW = 16: two instances share a warp)
-    const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
-    const int env = p.env_begin + blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
-    if (env >= p.n_envs) return;
-    constexpr int RC = KIND == TD_KIND_ATK ? kRngCacheAtk : kRngCacheDef;
-    Ctx<CELLS, GW, RC> w;
-    ctx_bind(w, td_smem + (size_t)group * p.smem_per_warp, p);               // [record | scratch] per instance
-    uint8_t *rec = p.records + (size_t)env * w.record_bytes();
+    constexpr int GW = W::G;
+    const int lane = w.lane;
     const td_step_io &io = p.io;
     const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
                                  !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
@@ -1240,7 +1265,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     gsync(w);
     finish_env_load(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
-    bool dirty = false;
 
     // cooldowns (TDDefense.py:38-39)
     w.atk_cd = max(w.atk_cd - 1, 0);
@@ -1357,19 +1381,34 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         dirty = true;
     }
     // Generator words for the next step: requested now, parked in the record after the observation went out.
-    constexpr int kRefill = (RC + GW - 1) / GW;
-    uint32_t next_word[kRefill];
 #pragma unroll
-    for (int q = 0; q < kRefill; ++q) next_word[q] = 0;
+    for (int q = 0; q < NREFILL; ++q) next_word[q] = 0;
     if (w.mt != nullptr) {
         w.ck = 0;
         w.cn = min(w.rng_words(), max(kMtWords - w.mt_pos, 0));
 #pragma unroll
-        for (int q = 0; q < kRefill; ++q)
+        for (int q = 0; q < NREFILL; ++q)
             if (lane + GW * q < w.cn)
                 asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word[q]) : "l"(w.mt + w.mt_pos + lane + GW * q) : "memory");
     }
-    if (io.obs_dev) write_obs(w, io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
+}
+
+template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const StepParams p)
+{
+    // one group of GW lanes per game instance (GW = 16: two instances share a warp)
+    const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
+    const int env = p.env_begin + blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
+    if (env >= p.n_envs) return;
+    constexpr int RC = KIND == TD_KIND_ATK ? kRngCacheAtk : kRngCacheDef;
+    Ctx<CELLS, GW, RC> w;
+    ctx_bind(w, td_smem + (size_t)group * p.smem_per_warp, p);               // [record | scratch] per instance
+    uint8_t *rec = p.records + (size_t)env * w.record_bytes();
+    bool dirty = false;
+    constexpr int kRefill = (RC + GW - 1) / GW;
+    uint32_t next_word[kRefill];
+    env_rules<KIND, MULTI, NCHUNK>(p, env, w, rec, dirty, next_word);
+    if (p.io.obs_dev) write_obs(w, p.io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
     gsync(w);
     if (w.mt != nullptr) {
 #pragma unroll

@@ -11,7 +11,7 @@ import numpy as np
 from . import params
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtd_b200.so")
+LIB_PATH = os.environ.get("TD_B200_LIB") or os.path.join(_HERE, "libtd_b200.so")   # override: kernel experiments
 
 NT, NLV, CLUSTER, ROADS, NCH, MAX_L = 4, 2, 8, 3, 45, 64
 CAP_TOWERS, CAP_ENEMIES = 32, 64
