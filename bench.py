@@ -24,6 +24,7 @@ WORKLOADS = {
     # name: (env id, kind, L, envs per GPU, multi_action, algorithmic bytes per env-step = SURVEY.md 8(d))
     "def-small": ("TD-def-small-v0", "def", 10, 65536, False, 4 * 45 * 100 + 8 + 24),
     "def-middle-multi": ("TD-def-middle-v0", "def", 20, 32768, True, 4 * 45 * 400 + 19200 + 19216),
+    "def-middle-multi-sparse": ("TD-def-middle-v0", "def", 20, 32768, True, 4 * 45 * 400 + 19200 + 19216),
     "atk-small": ("TD-atk-small-v0", "atk", 10, 65536, False, 4 * 45 * 100 + 192 + 208),
     "2p-large": ("TD-2p-large-v0", "2p", 30, 16384, False, 4 * 45 * 900 + 200 + 216),
     "def-middle": ("TD-def-middle-v0", "def", 20, 32768, False, 4 * 45 * 400 + 8 + 24),
@@ -52,7 +53,8 @@ def config_of(args, n_envs):
     env_id, kind, L, _, multi, bpe = WORKLOADS[args.workload]
     return {
         "workload": "%s batched, %d envs/GPU, %s actions, scripted opponent lv1, auto-reset from a map pool"
-                    % (env_id, n_envs, "Box(6,L,L) multi" if multi else
+                    % (env_id, n_envs, ("Box(6,L,L) multi, flags 1 with p=0.01" if args.workload.endswith("sparse") else
+                                          "Box(6,L,L) multi, uniform {0,1,2}") if multi else
                        ("Discrete" if kind == "def" else "cluster (3,8)" if kind == "atk" else "Dict")),
         "env_id": env_id, "map_size": L, "envs_per_gpu": n_envs,
         "global_envs": n_envs * args.gpus, "parallelism": "env-shard x%d" % args.gpus,
@@ -235,7 +237,10 @@ def main():
     def_pool = atk_pool = None
     if kind != "atk":
         if multi:
-            def_pool = torch.randint(0, 3, (4, n_envs, 6, L, L), dtype=torch.int64, device=dev, generator=g)
+            if args.workload.endswith("sparse"):     # SURVEY 8(d) config 3, second variant: each flag 1 with p = 0.01
+                def_pool = (torch.rand((4, n_envs, 6, L, L), device=dev, generator=g) < 0.01).to(torch.int64)
+            else:                                    # action_space.sample(): uniform {0, 1, 2}
+                def_pool = torch.randint(0, 3, (4, n_envs, 6, L, L), dtype=torch.int64, device=dev, generator=g)
         else:
             def_pool = torch.randint(0, 6 * L * L + 1, (A, n_envs), dtype=torch.int64, device=dev, generator=g)
     if kind != "def":

@@ -87,6 +87,11 @@ def smart_defender_action(o, rs, p_nop=0.3, p_uniform=0.2):
     return (4 if kind < 9 else 5) * cells + tw.loc
 
 
+def uniform_multi_action(L, rs):
+    """Box(0, 2, (6, L, L), int64).sample(): the distribution of BASELINE config 3."""
+    return rs.randint(0, 3, size=(6, L, L)).astype(np.int64)
+
+
 def sparse_multi_action(L, rs, p=0.02):
     a = (rs.random_sample((6, L, L)) < p).astype(np.int64)
     a[rs.random_sample((6, L, L)) < p] = 2
@@ -139,7 +144,7 @@ def compare_state(tag, eng, rec, o):
 
 
 def run_parity(kind, L, n_envs, steps, seed=0, multi=False, opponent="device", difficulty=1, cfg_overrides=None,
-               check_state_every=1, device=0, use_host_api=False):
+               check_state_every=1, device=0, use_host_api=False, multi_mode="sparse"):
     """Step `n_envs` instances on the GPU and in the oracle; compare everything each step.
 
     opponent: "device" (on-device CPython-compatible generator), "stream" (host-resolved type/road
@@ -200,7 +205,8 @@ def run_parity(kind, L, n_envs, steps, seed=0, multi=False, opponent="device", d
                     a_def[i] = 6 * cells
                 continue
             if kind != "atk":
-                a_def[i] = sparse_multi_action(L, rs) if multi else smart_defender_action(o, rs)
+                a_def[i] = ((uniform_multi_action(L, rs) if multi_mode == "uniform" else sparse_multi_action(L, rs))
+                            if multi else smart_defender_action(o, rs))
             if kind != "def":
                 a_atk[i] = attacker_action(rs)
             if kind == "def" and opponent == "stream":

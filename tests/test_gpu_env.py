@@ -379,3 +379,53 @@ def test_param_config_reaches_the_device_like_the_reference():
             mine.close()
     finally:
         G.paramConfig(**old)
+
+
+def _round_road_episode(env, t, num_enemy):
+    """The caller loop of the reference's balance script (balance.py:95-121), one episode."""
+    done, mem, road, total = False, None, 0, 0.0
+    while not done:
+        if mem is not None:
+            act = mem
+        else:
+            act = np.full((3, 8), 4, np.int64)
+            act[road, :num_enemy] = t
+            road = road + 1 if road + 1 < env.num_roads else 0
+        _, r, done, info = env.step(act)
+        mem = act if 2 in info["FailCode"] else None            # FC.COST_SHORTAGE
+        total += r
+    return info["Win"], total
+
+
+def test_balance_scripts_through_facade_and_batched_agent():
+    """the balance.py attack scripts. The single-env loop gives the same episodes through the
+    reference env and the façade; the batched agent reproduces the façade's first episodes env by env."""
+    import gym_td_b200 as G
+    from gym_td_b200 import balance as B
+    from oracle import ref_loader
+    np.seterr(all="ignore")
+    t, num_enemy = 1, 6                                         # min(100 // 15, 8)
+    if ref_loader.available():
+        from oracle import ref_harness as RH
+        ref_loader.load()
+        ref = RH.make_env("atk", 10, 1024)
+        random.seed(1024)
+        w1, r1 = _round_road_episode(ref, t, num_enemy)
+        mine = G.make("TD-atk-small-v0", seed=1024)
+        random.seed(1024)
+        w2, r2 = _round_road_episode(mine, t, num_enemy)
+        mine.close()
+        assert repr(w1) == repr(w2) and repr(float(r1)) == repr(float(r2))
+    K, base = 6, 4242
+    vec = G.make_vec("TD-atk-small-v0", K, seed=base)
+    agent = B.RoundRoadAttacker(vec, t)
+    assert agent.num_enemy == num_enemy
+    wins, rets = B.evaluate(vec, agent, 1)
+    wins, rets = wins.cpu().numpy(), rets.cpu().numpy()
+    for i in range(K):
+        env = G.make("TD-atk-small-v0", seed=int(vec.map_seeds[i]))
+        random.seed(base + i)
+        w, r = _round_road_episode(env, t, num_enemy)
+        env.close()
+        assert int(wins[i, 0]) == int(bool(w)) and abs(rets[i, 0] - r) < 1e-9, (i, wins[i, 0], w, rets[i, 0], r)
+    vec.close()

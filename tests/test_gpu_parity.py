@@ -45,6 +45,13 @@ def test_def_multi_action(L):
     assert PU.run_parity("def", L, n_envs=24, steps=600, seed=L + 4, multi=True, opponent="device") > 2000
 
 
+def test_def_multi_action_uniform_sample():
+    """BASELINE config 3's action distribution: action_space.sample() = uniform {0, 1, 2} on every flag
+    (towers are built, upgraded and destructed within the same step almost everywhere)."""
+    assert PU.run_parity("def", 20, n_envs=12, steps=300, seed=77, multi=True, opponent="device",
+                         multi_mode="uniform") > 1000
+
+
 def test_multi_multi_action():
     assert PU.run_parity("2p", 20, n_envs=16, steps=600, seed=9, multi=True, opponent="none") > 2000
 
