@@ -282,6 +282,61 @@ def test_full_size_determinism_and_replayed_subset():
             assert np.array_equal(sub1[k][0][i].view(np.uint32), oenv.get_states().view(np.uint32)), (i, k)
 
 
+@pytest.mark.parametrize("kind,L,N,multi", [("atk", 10, 65536, False), ("def", 20, 32768, True), ("2p", 30, 16384, False)])
+def test_full_size_properties_of_the_other_baseline_configs(kind, L, N, multi):
+    """BASELINE.json configs 3-5 at their full per-GPU sizes: bitwise determinism of two runs (a checksum of
+    the per-step checksums) and size-independent invariants tying every observation to its env record."""
+    import torch
+    from gym_td_b200 import engine as E
+    from gym_td_b200.vec_env import TDVecEnv
+    K = 30
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a_atk = torch.randint(0, 5, (4, N, 3, 8), dtype=torch.int64, device="cuda", generator=g) if kind != "def" else None
+    if kind == "atk":
+        a_def = None
+    elif multi:
+        a_def = (torch.rand((2, N, 6, L, L), device="cuda", generator=g) < 0.01).to(torch.int64)
+    else:
+        a_def = torch.randint(0, 6 * L * L + 1, (4, N), dtype=torch.int64, device="cuda", generator=g)
+
+    def action(k):
+        d = a_def[k % a_def.shape[0]] if a_def is not None else None
+        a = a_atk[k % 4] if a_atk is not None else None
+        return d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+
+    def run():
+        env = TDVecEnv(kind, L, N, seed=3, auto_reset=True, multi_action=multi)
+        env.reset()
+        digest = 0
+        for k in range(K):
+            obs, rew, done, info = env.step(action(k))
+            digest = (digest * 1000003 + obs.view(torch.int32).sum(dtype=torch.int64).item()
+                      + 31 * rew.view(torch.int64).sum().item() + 7 * int(done.sum().item())) % (1 << 61)
+        M = 1024
+        blob = env.engine.get_state_raw(0, M)
+        hdr = np.stack([b[:64].view(E.HEADER_DTYPE)[0] for b in blob])
+        o = env.obs[:M].cpu().numpy()
+        flags = env.stats()
+        env.close()
+        return digest, hdr, o, flags
+
+    d1, hdr, o, st = run()
+    d2, _, _, _ = run()
+    assert d1 == d2
+    assert np.array_equal(o[:, 11, 0, 0], (hdr["cost_def"] / 100.0).astype(np.float32))
+    assert np.array_equal(o[:, 12, L - 1, 0], (hdr["cost_atk"] / 100.0).astype(np.float32))
+    assert np.array_equal(o[:, 13, 0, L - 1], (hdr["steps"] / 1200).astype(np.float32))
+    assert np.array_equal(o[:, 5, 1, 1], (hdr["base_LP"] / 5).astype(np.float32))
+    assert (o[:, 10] == 0).all()
+    # one-hot planes against the list lengths of the record: towers by level (15-16) and by type (17-20),
+    # enemies through the count planes (37-40 hold count / 8 per cell and type)
+    assert np.array_equal(o[:, 15:17].sum(axis=(1, 2, 3)), hdr["n_towers"].astype(np.float32))
+    assert np.array_equal(o[:, 17:21].sum(axis=(1, 2, 3)), hdr["n_towers"].astype(np.float32))
+    assert np.array_equal(o[:, 37:41].sum(axis=(1, 2, 3)) * 8, hdr["n_enemies"].astype(np.float32))
+    assert (o[:, 4].sum(axis=(1, 2)) == 1).all() and (o[:, 6:9].sum(axis=(1, 2, 3)) >= 1).all()
+    assert (o[:, 25:29] <= o[:, 29:33]).all()                         # min ratio <= max ratio wherever enemies stand
+
+
 @pytest.mark.parametrize("kind", ["def", "atk"])
 def test_checkpoint_resume_is_bit_identical(kind):
     import torch
