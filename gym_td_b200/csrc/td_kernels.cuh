@@ -365,9 +365,9 @@ __device__ __forceinline__ void load_env(W &w, const StepParams &p, const uint8_
 
 // Write back the header block (incl. the word cache), the changed maps and the live list prefixes.
 template <class W>
-__device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *rec, bool map6_dirty)
+__device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *rec, bool map6_dirty, bool push = true)
 {
-    push_header(w);
+    if (push) push_header(w);
     gsync(w);
     const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : w.hdr_bytes());
     warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
@@ -1068,7 +1068,11 @@ __device__ __forceinline__ void obs_prepare(W &w)
         else if (lane == 3) { num = (double)w.steps; den = (double)cc.max_steps; plane = 13; }
         else if (lane < 8) { num = w.cost_def; den = cc.enemy_cost[lane - 4][0]; plane = 41 + lane - 4; }
         else if (lane < 12) { plane = 21 + lane - 8; }
-        double qv = num / den;
+        // a zero numerator (idle lanes, an empty purse, a fallen base) would send the whole warp through the
+        // division's slow path: divide 1.0 instead and put the exact +0.0 back
+        const bool zero = num == 0.0;
+        double qv = (zero ? 1.0 : num) / den;
+        if (zero) qv = 0.0;
         if (lane >= 4 && lane < 8) qv *= 0.125;                    // "/ max_cluster_length": exact power of two
         float val = (float)qv;
         if (lane == 0 && cc.base_LP < 0) val = 1.f;
@@ -1408,6 +1412,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     constexpr int kRefill = (RC + GW - 1) / GW;
     uint32_t next_word[kRefill];
     env_rules<KIND, MULTI, NCHUNK>(p, env, w, rec, dirty, next_word);
+    // The header scalars go back to the slice before the observation is written: their registers are free
+    // during the store phase (a spilled one cost a local-memory reload behind 18 KB of stores: 8 % of the step).
+    push_header(w);
     if (p.io.obs_dev) write_obs(w, p.io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
     gsync(w);
     if (w.mt != nullptr) {
@@ -1415,7 +1422,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         for (int q = 0; q < kRefill; ++q)
             if (lane + GW * q < RC) const_cast<uint32_t *>(w.rng_cache())[lane + GW * q] = next_word[q];
     }
-    store_env(w, p, rec, dirty);
+    store_env(w, p, rec, dirty, false);
 }
 
 // reset (mask / explicit map ids) and observation-only kernels
