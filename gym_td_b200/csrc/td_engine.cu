@@ -160,6 +160,10 @@ static int upload_config(td_handle *h, const td_config *c)
         volatile double prog = (double)sidx / (double)c->max_episode_steps;
         if (prog >= c->enemy_upgrade_at) { d.upgrade_step = sidx; break; }
     }
+    for (int lv = 0; lv < TD_NLV; ++lv) {
+        d.min_enemy_cost[lv] = d.enemy_cost[0][lv];
+        for (int t = 1; t < TD_NTYPES; ++t) d.min_enemy_cost[lv] = std::min(d.min_enemy_cost[lv], d.enemy_cost[t][lv]);
+    }
     d.frozen_time = c->frozen_time;
     d.base_LP = c->base_LP < 0 ? -1 : c->base_LP;
     d.tower_distance = c->tower_distance;
@@ -277,7 +281,7 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->off_enemies = h->off_towers + TD_CAP_TOWERS * kTowerBytes;
     h->record_bytes = h->off_enemies + TD_CAP_ENEMIES * kEnemyBytes;
     h->scratch_off = h->record_bytes;
-    int scratch = std::max(768, std::max(h->cells_pad, round16(2 * std::min(h->cells, 6 * map_size))));
+    int scratch = std::max(1024, std::max(h->cells_pad, round16(2 * std::min(h->cells, 6 * map_size)) + 256));   // + shuffle word buffer
     h->smem_per_warp = h->record_bytes + scratch;
     h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
     h->opponent_seeded = false; h->steps = 0;

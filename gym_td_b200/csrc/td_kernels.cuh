@@ -82,6 +82,7 @@ struct DevConfig {
     double reward_kill, penalty_leak, reward_time, rate_init, rate_final, def_rate, upgrade_at;
     int frozen_time, base_LP, tower_distance, atk_interval, def_interval, max_steps;
     int upgrade_step;       // smallest s with (double)s / max_steps >= enemy_upgrade_at (TDBoard.py:201 without the division)
+    double min_enemy_cost[TD_NLV];   // cheapest enemy type per level: below it every remaining cluster slot fails
 };
 
 __constant__ DevConfig cc;
@@ -124,6 +125,7 @@ template <int CELLS, int GW, int RC = 0>
 struct Ctx {
     static constexpr int kCells = CELLS;
     static constexpr int G = GW;
+    static constexpr int kRngWords = RC;
     unsigned gmask;            // the warp lanes of this env's group
     int gbase;                 // first warp lane of the group
     static constexpr int kL = CELLS == 100 ? 10 : CELLS == 400 ? 20 : CELLS == 900 ? 30 : 0;
@@ -416,6 +418,47 @@ __device__ __forceinline__ int py_randbelow(W &w, int n)
     return (int)r;
 }
 
+// random.shuffle(list) (for i in reversed(range(1, n)): j = randbelow(i + 1); swap) on a uint16 list in shared
+// memory.  The draws are serial by definition (rejections shift every later draw), so one lane runs the whole
+// loop alone over a buffer of tempered words the group fetched for it -- a fifth of the instructions of the
+// same loop with a group-wide draw per element.  `buf` holds kShufflePeek words.
+constexpr int kShufflePeek = 64;
+template <class W>
+__device__ __forceinline__ void py_shuffle_u16(W &w, uint16_t *list, int n, uint32_t *buf)
+{
+    const int pos0 = w.hdr()->rng_pos;               // generator position the cached words start at
+    int i = n - 1;
+    while (i >= 1) {
+        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane, W::G, w.gmask); w.mt_pos = 0; w.cn = 0; }
+        const int avail = min(kShufflePeek, kMtWords - w.mt_pos);
+        for (int q = w.lane; q < avail; q += W::G) {
+            const int a = w.mt_pos + q;
+            const uint32_t y = (a >= pos0 && a - pos0 < w.cn) ? w.rng_cache()[a - pos0] : w.mt[a];
+            buf[q] = mt_temper(y);
+        }
+        gsync(w);
+        int used = 0;
+        if (w.lane == 0) {
+            while (i >= 1 && used < avail) {
+                const uint32_t r = buf[used++] >> __clz(i + 1);
+                if (r <= (uint32_t)i) {
+                    const uint16_t t = list[i];
+                    list[i] = list[r];
+                    list[r] = t;
+                    --i;
+                }
+            }
+        }
+        used = gshfl(w, used, 0);
+        i = gshfl(w, i, 0);
+        w.mt_pos += used;
+        gsync(w);
+    }
+    // the lane window is stale now; the word cache continues where the shuffle stopped
+    w.win_k = w.win_n = 0;
+    w.ck = w.mt_pos >= pos0 ? min(w.cn, w.mt_pos - pos0) : w.cn;     // behind pos0: twisted this step, cache is stale
+}
+
 template <class W>
 __device__ __forceinline__ double py_random(W &w)
 {
@@ -645,7 +688,9 @@ __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, 
     unsigned todo = ~b2 & 0xffu;                     // slots holding a real type (0..3)
     const bool tried = todo != 0;
     unsigned ok = 0, poor = 0;
+    const double cheapest = cc.min_enemy_cost[lv];
     while (todo) {
+        if (w.cost_atk < cheapest) { poor |= todo; break; }      // an empty purse fails every remaining slot alike
         const int k = __ffs(todo) - 1;
         todo &= todo - 1;
         const int t = ((b0 >> k) & 1) | (((b1 >> k) & 1) << 1);
@@ -774,11 +819,11 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
             n += __popc(b);
         }
         gsync(w);
-        for (int i = n - 1; i >= 1; --i) {                   // random.shuffle
-            int j = py_randbelow(w, i + 1);
-            if (w.lane == 0) { uint16_t t = list[i]; list[i] = list[j]; list[j] = t; }
+        {
+            const int buf_off = (2 * n + 15) & ~15;
+            TD_CHECK(w, buf_off + 4 * kShufflePeek <= w.pp->smem_per_warp - w.record_bytes());
+            py_shuffle_u16(w, list, n, reinterpret_cast<uint32_t *>(w.scratch() + buf_off));
         }
-        gsync(w);
         if (difficulty != 2) t = py_randbelow(w, TD_NTYPES);
         for (int k = 0; k < n; ++k) {
             int di = py_randbelow(w, 25);
@@ -1060,7 +1105,7 @@ __device__ __forceinline__ void obs_prepare(W &w)
     // lane 0 -> plane 5, 1 -> 11, 2 -> 12, 3 -> 13, 4..7 -> 41..44 (cost_def / enemy_cost / 8), 8..11 -> 21..24.
     float *pv = reinterpret_cast<float *>(w.scratch()) + 64;         // [48], behind ratio[64]
     {
-        double num = 0.0, den = 1.0;
+        double num = 1.0, den = 1.0;      // idle lanes divide 1 by 1: a zero numerator takes the division's slow-path call
         int plane = 47;
         if (lane == 0) { num = (double)w.base_LP; den = (double)cc.base_LP; plane = 5; }
         else if (lane == 1) { num = w.cost_def; den = cc.max_cost; plane = 11; }
@@ -1068,11 +1113,7 @@ __device__ __forceinline__ void obs_prepare(W &w)
         else if (lane == 3) { num = (double)w.steps; den = (double)cc.max_steps; plane = 13; }
         else if (lane < 8) { num = w.cost_def; den = cc.enemy_cost[lane - 4][0]; plane = 41 + lane - 4; }
         else if (lane < 12) { plane = 21 + lane - 8; }
-        // a zero numerator (idle lanes, an empty purse, a fallen base) would send the whole warp through the
-        // division's slow path: divide 1.0 instead and put the exact +0.0 back
-        const bool zero = num == 0.0;
-        double qv = (zero ? 1.0 : num) / den;
-        if (zero) qv = 0.0;
+        double qv = num / den;
         if (lane >= 4 && lane < 8) qv *= 0.125;                    // "/ max_cluster_length": exact power of two
         float val = (float)qv;
         if (lane == 0 && cc.base_LP < 0) val = 1.f;
@@ -1088,13 +1129,32 @@ __device__ __forceinline__ void obs_prepare(W &w)
 // Step 2: the dense planes of the env whose record sits in w.slice, written by NT cooperating threads
 // (tid in [0, NT)): NT = W::G for one group per env, NT = the CTA size for the CTA-cooperative sweep.
 // Only the slice pointers of `w` are used.
+// dist / maxd for the distance plane, correctly rounded like the IEEE division the reference's float32 array
+// performs, without the division's range check: a zero numerator (every off-road cell) sends __fdiv_rn through
+// its slow-path call.  One refined reciprocal per env, then quotient + exact remainder + correction per cell
+// (Markstein); tests/test_host.py proves it for all 0 <= a <= 255, 1 <= b <= 256 and any 1-ulp reciprocal.
+struct SmallDiv {
+    float b, r;
+    __device__ __forceinline__ explicit SmallDiv(float den) : b(den)
+    {
+        float x;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(x) : "f"(den));
+        r = __fmaf_rn(x, __fmaf_rn(-den, x, 1.f), x);
+    }
+    __device__ __forceinline__ float operator()(float a) const
+    {
+        const float q = __fmul_rn(a, r);
+        return __fmaf_rn(__fmaf_rn(-b, q, a), r, q);
+    }
+};
+
 template <int NT, class W>
 __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
 {
     constexpr int CELLS = W::kCells;
     const int cells = CELLS > 0 ? CELLS : w.ncells();
     const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
-    const float maxd = (float)w.mh()->maxd_p1;
+    const SmallDiv by_maxd((float)w.mh()->maxd_p1);
     const float *pv = reinterpret_cast<const float *>(w.scratch()) + 64;
     if (CELLS > 0 && vec) {
         constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
@@ -1112,8 +1172,8 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
                 for (int k = 0; k < 4; ++k)
                     TD_ST(o4 + k * C4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
                                                         (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
-                TD_ST(o4 + 9 * C4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
-                                                    __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
+                TD_ST(o4 + 9 * C4 + q, make_float4(by_maxd((float)d.x), by_maxd((float)d.y),
+                                                    by_maxd((float)d.z), by_maxd((float)d.w)));
                 TD_ST(o4 + 14 * C4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
                                                      m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
             }
@@ -1148,8 +1208,8 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
         fill_planes(o, 6, 3, cells, 0.f, tid, NT);
         for (int q = tid; q < c4; q += NT) {
             uchar4 d = db[q];
-            TD_ST(o4 + 9 * c4 + q, make_float4(__fdiv_rn((float)d.x, maxd), __fdiv_rn((float)d.y, maxd),
-                                                __fdiv_rn((float)d.z, maxd), __fdiv_rn((float)d.w, maxd)));
+            TD_ST(o4 + 9 * c4 + q, make_float4(by_maxd((float)d.x), by_maxd((float)d.y),
+                                                by_maxd((float)d.z), by_maxd((float)d.w)));
         }
         fill_planes(o, 10, 1, cells, 0.f, tid, NT);
         for (int k = 11; k < 14; ++k) fill_planes(o, k, 1, cells, pv[k], tid, NT);
@@ -1167,7 +1227,7 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
             uint8_t c = w.cells()[q];
 #pragma unroll
             for (int k = 0; k < 4; ++k) TD_ST(o + (size_t)k * cells + q, (float)((c >> k) & 1));
-            TD_ST(o + (size_t)9 * cells + q, __fdiv_rn((float)w.dist()[q], maxd));
+            TD_ST(o + (size_t)9 * cells + q, by_maxd((float)w.dist()[q]));
             TD_ST(o + (size_t)14 * cells + q, w.map6()[q] == 0 ? 1.f : 0.f);
         }
         for (int k = 4; k < TD_NCHANNELS; ++k)
@@ -1242,11 +1302,10 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 #endif
 
 // One env's rules for one step: load the record, apply the actions / scripted opponent, advance the board, emit
-// the per-env outputs, auto-reset.  Leaves the updated record in the slice and requests the generator words of
-// the next step (next_word, parked in the record by the caller once the observation went out).
-template <int KIND, bool MULTI, int NCHUNK, class W, int NREFILL>
-__device__ __forceinline__ void env_rules(const StepParams &p, const int env, W &w, uint8_t *rec, bool &dirty,
-                                          uint32_t (&next_word)[NREFILL])
+// the per-env outputs, auto-reset.  Leaves the updated record in the slice and starts the asynchronous copy of
+// the next step's generator words into the slice's word cache (the caller waits for it before store_env).
+template <int KIND, bool MULTI, int NCHUNK, class W>
+__device__ __forceinline__ void env_rules(const StepParams &p, const int env, W &w, uint8_t *rec, bool &dirty)
 {
     constexpr int GW = W::G;
     const int lane = w.lane;
@@ -1384,17 +1443,23 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
         reset_env(w, p, next, true);
         dirty = true;
     }
-    // Generator words for the next step: requested now, parked in the record after the observation went out.
-#pragma unroll
-    for (int q = 0; q < NREFILL; ++q) next_word[q] = 0;
+    // Generator words for the next step: copied global -> shared straight into the slice's word cache (this
+    // step's draws are done with it), asynchronously, so that no register waits for them behind the observation.
     if (w.mt != nullptr) {
         w.ck = 0;
         w.cn = min(w.rng_words(), max(kMtWords - w.mt_pos, 0));
+        constexpr int kRefill = (W::kRngWords + GW - 1) / GW;
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(w.rng_cache());
 #pragma unroll
-        for (int q = 0; q < NREFILL; ++q)
-            if (lane + GW * q < w.cn)
-                asm volatile("ld.global.u32 %0, [%1];" : "=r"(next_word[q]) : "l"(w.mt + w.mt_pos + lane + GW * q) : "memory");
+        for (int q = 0; q < kRefill; ++q) {
+            const int k = lane + GW * q;
+            if (k < w.cn)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u * k), "l"(w.mt + w.mt_pos + k) : "memory");
+            else if (k < W::kRngWords)
+                const_cast<uint32_t *>(w.rng_cache())[k] = 0u;
+        }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
 template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW>
@@ -1409,19 +1474,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
     ctx_bind(w, td_smem + (size_t)group * p.smem_per_warp, p);               // [record | scratch] per instance
     uint8_t *rec = p.records + (size_t)env * w.record_bytes();
     bool dirty = false;
-    constexpr int kRefill = (RC + GW - 1) / GW;
-    uint32_t next_word[kRefill];
-    env_rules<KIND, MULTI, NCHUNK>(p, env, w, rec, dirty, next_word);
+    env_rules<KIND, MULTI, NCHUNK>(p, env, w, rec, dirty);
     // The header scalars go back to the slice before the observation is written: their registers are free
     // during the store phase (a spilled one cost a local-memory reload behind 18 KB of stores: 8 % of the step).
     push_header(w);
     if (p.io.obs_dev) write_obs(w, p.io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells());
-    gsync(w);
-    if (w.mt != nullptr) {
-#pragma unroll
-        for (int q = 0; q < kRefill; ++q)
-            if (lane + GW * q < RC) const_cast<uint32_t *>(w.rng_cache())[lane + GW * q] = next_word[q];
-    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");          // the next step's generator words are in the slice
     store_env(w, p, rec, dirty, false);
 }
 

@@ -49,3 +49,40 @@ def test_shard_ranges_partition_the_envs():
         assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
     assert dist.env_seeds(5, 2, 5) == [7, 8, 9]
+
+
+def test_distance_plane_division_is_correctly_rounded_for_every_operand():
+    """The step kernel writes dist / (max dist + 1) with a hand-rolled float32 division (SmallDiv in
+    csrc/td_kernels.cuh: refined reciprocal, quotient, exact remainder, correction).  Exact rational
+    arithmetic with round-to-nearest-even shows it returns the IEEE quotient for every 0 <= a <= 255,
+    1 <= b <= 256 and for any hardware reciprocal within one ulp of 1 / b."""
+    from fractions import Fraction
+
+    def rn(x):                                      # Fraction -> nearest float32 (ties to even), as a Fraction
+        if x == 0:
+            return Fraction(0)
+        s, x = (-1 if x < 0 else 1), abs(x)
+        e = x.numerator.bit_length() - x.denominator.bit_length()
+        if Fraction(2) ** e > x:
+            e -= 1
+        ulp = Fraction(2) ** (e - 23)
+        q, r = divmod(x, ulp)
+        q = int(q)
+        if r * 2 > ulp or (r * 2 == ulp and q & 1):
+            q += 1
+        return s * q * ulp
+
+    def fma(a, b, c):
+        return rn(a * b + c)
+
+    for b_int in range(1, 257):
+        b = Fraction(b_int)
+        r0 = rn(1 / b)
+        ulp = Fraction(2) ** (r0.numerator.bit_length() - r0.denominator.bit_length() - 24)
+        for x in (r0, r0 + ulp, r0 - ulp):         # rcp.approx: anything within 1 ulp
+            r = fma(x, fma(-b, x, Fraction(1)), x)
+            for a_int in range(0, 256):
+                a = Fraction(a_int)
+                q = rn(a * r)
+                got = fma(fma(-b, q, a), r, q)
+                assert got == rn(a / b), (a_int, b_int)
