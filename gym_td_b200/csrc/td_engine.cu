@@ -282,6 +282,7 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->record_bytes = h->off_enemies + TD_CAP_ENEMIES * kEnemyBytes;
     h->scratch_off = h->record_bytes;
     int scratch = std::max(1024, std::max(h->cells_pad, round16(2 * std::min(h->cells, 6 * map_size)) + 256));   // + shuffle word buffer
+    if (env_kind != TD_KIND_2P) scratch += kTwistStageBytes;        // staging area of the opponent generator's twist
     h->smem_per_warp = h->record_bytes + scratch;
     h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
     h->opponent_seeded = false; h->steps = 0;

@@ -63,6 +63,7 @@ constexpr int kTowerBytes = 16;
 constexpr int kEnemyBytes = 24;
 constexpr int kMapHdrBytes = 16;
 constexpr int kMtWords = 624;
+constexpr int kTwistStageBytes = kMtWords * 4;   // staging area of the generator regeneration (tail of a slice)
 constexpr int kSpecTowers = 16;           // speculatively staged list prefixes
 constexpr int kSpecEnemies = 16;
 
@@ -163,6 +164,11 @@ struct Ctx {
     __device__ __forceinline__ td_tower_rec *tw() const { return reinterpret_cast<td_tower_rec *>(slice + off_towers()); }
     __device__ __forceinline__ td_enemy_rec *en() const { return reinterpret_cast<td_enemy_rec *>(slice + off_enemies()); }
     __device__ __forceinline__ uint8_t *scratch() const { return slice + record_bytes(); }
+    // tail of the slice (envs with a scripted opponent only): staging area of the generator regeneration
+    __device__ __forceinline__ uint32_t *twist_stage() const
+    {
+        return reinterpret_cast<uint32_t *>(slice + pp->smem_per_warp - kTwistStageBytes);
+    }
 };
 
 // group-level primitives: ballots are returned relative to the group (bit 0 = group lane 0)
@@ -290,6 +296,18 @@ __device__ __noinline__ void mt_twist(uint32_t *mt, int lane, int stride, unsign
     __syncwarp(gmask);
 }
 
+// The same through shared memory: the 20 dependent chunks of the regeneration cost one HBM round trip each when
+// run on the state in place (40 us per twist under load); staged, the state travels once in and once out.
+// gmt is 16-byte aligned (624 words per env), smt is a 2496-byte staging area in the group's slice.
+__device__ __noinline__ void mt_twist_staged(uint32_t *gmt, uint32_t *smt, int lane, int stride, unsigned gmask)
+{
+    for (int q = lane; q < kMtWords / 4; q += stride) reinterpret_cast<int4 *>(smt)[q] = reinterpret_cast<const int4 *>(gmt)[q];
+    __syncwarp(gmask);
+    mt_twist(smt, lane, stride, gmask);
+    for (int q = lane; q < kMtWords / 4; q += stride) reinterpret_cast<int4 *>(gmt)[q] = reinterpret_cast<const int4 *>(smt)[q];
+    __syncwarp(gmask);
+}
+
 __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 {
     y ^= y >> 11;
@@ -312,7 +330,7 @@ __device__ __forceinline__ void mt_fill_window(W &w)
         w.ck += n;
         w.win_n = n;
     } else {
-        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane, W::G, w.gmask); w.mt_pos = 0; }
+        if (w.mt_pos >= kMtWords) { mt_twist_staged(w.mt, w.twist_stage(), w.lane, W::G, w.gmask); w.mt_pos = 0; }
         const int n = min(W::G, kMtWords - w.mt_pos);
         if (w.lane < n) y = w.mt[w.mt_pos + w.lane];
         w.win_n = n;
@@ -429,8 +447,10 @@ __device__ __forceinline__ void py_shuffle_u16(W &w, uint16_t *list, int n, uint
     const int pos0 = w.hdr()->rng_pos;               // generator position the cached words start at
     int i = n - 1;
     while (i >= 1) {
-        if (w.mt_pos >= kMtWords) { mt_twist(w.mt, w.lane, W::G, w.gmask); w.mt_pos = 0; w.cn = 0; }
-        const int avail = min(kShufflePeek, kMtWords - w.mt_pos);
+        if (w.mt_pos >= kMtWords) { mt_twist_staged(w.mt, w.twist_stage(), w.lane, W::G, w.gmask); w.mt_pos = 0; w.cn = 0; }
+        int avail = min(kShufflePeek, kMtWords - w.mt_pos);
+        const int cached = w.mt_pos >= pos0 ? w.cn - (w.mt_pos - pos0) : 0;
+        if (cached > 0) avail = min(avail, cached);             // stay inside the word cache while it lasts: no HBM trip
         for (int q = w.lane; q < avail; q += W::G) {
             const int a = w.mt_pos + q;
             const uint32_t y = (a >= pos0 && a - pos0 < w.cn) ? w.rng_cache()[a - pos0] : w.mt[a];
@@ -821,7 +841,7 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
         gsync(w);
         {
             const int buf_off = (2 * n + 15) & ~15;
-            TD_CHECK(w, buf_off + 4 * kShufflePeek <= w.pp->smem_per_warp - w.record_bytes());
+            TD_CHECK(w, buf_off + 4 * kShufflePeek <= w.pp->smem_per_warp - w.record_bytes() - kTwistStageBytes);
             py_shuffle_u16(w, list, n, reinterpret_cast<uint32_t *>(w.scratch() + buf_off));
         }
         if (difficulty != 2) t = py_randbelow(w, TD_NTYPES);
