@@ -1263,11 +1263,20 @@ __device__ __forceinline__ void obs_sparse(W &w, float *o)
     constexpr int CELLS = W::kCells;
     const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells();
     // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
-    float *ratio = reinterpret_cast<float *>(w.scratch());       // [64]
     const int ne = w.ne;
-    for (int e = lane; e < ne; e += W::G) {
-        const td_enemy_rec &x = w.en()[e];
-        ratio[e] = (float)(x.LP / cc.enemy_LP[x.type_lv & 3][x.type_lv >> 2]);
+    const bool one_pass = W::G == 32 && ne <= 32;                // every enemy has its own lane
+    float *ratio = reinterpret_cast<float *>(w.scratch());       // [64], only for the general path
+    float mine = 0.f;
+    if (one_pass) {
+        if (lane < ne) {
+            const td_enemy_rec &x = w.en()[lane];
+            mine = (float)(x.LP / cc.enemy_LP[x.type_lv & 3][x.type_lv >> 2]);
+        }
+    } else {
+        for (int e = lane; e < ne; e += W::G) {
+            const td_enemy_rec &x = w.en()[e];
+            ratio[e] = (float)(x.LP / cc.enemy_LP[x.type_lv & 3][x.type_lv >> 2]);
+        }
     }
     gsync(w);   // also orders the dense stores above before the sparse stores below
 #ifdef TD_EXP_NO_SPARSE
@@ -1279,6 +1288,34 @@ __device__ __forceinline__ void obs_sparse(W &w, float *o)
         const td_tower_rec &T = w.tw()[t];
         o[(size_t)(15 + (T.type_lv >> 2)) * cells + T.loc] = 1.f;
         o[(size_t)(17 + (T.type_lv & 3)) * cells + T.loc] = 1.f;
+    }
+    if (one_pass) {
+        // lanes of one (cell, type) group find each other with one match instruction; every lane then folds its
+        // group's ratios in list order (ascending lane): as many rounds as the largest group has members
+        const bool have = lane < ne;
+        const int loc = have ? w.en()[lane].loc : 0, ty = have ? (w.en()[lane].type_lv & 3) : 0;
+        TD_CHECK(w, loc < cells && ne <= w.ecap);
+        const unsigned group = __match_any_sync(kFull, have ? (unsigned)(loc * 4 + ty) : 0x80000000u + lane);
+        unsigned todo = group;
+        float mn = 1.f, mx = 0.f, sum = 0.f;
+        while (__any_sync(kFull, todo != 0u)) {
+            const int j = todo ? __ffs(todo) - 1 : lane;
+            const float r = __shfl_sync(kFull, mine, j);
+            if (todo) {
+                mn = r < mn ? r : mn;
+                mx = r > mx ? r : mx;
+                sum = __fadd_rn(sum, r);
+                todo &= todo - 1u;
+            }
+        }
+        if (have && lane == __ffs(group) - 1) {
+            const float cnt = (float)__popc(group);
+            o[(size_t)(25 + ty) * cells + loc] = mn;
+            o[(size_t)(29 + ty) * cells + loc] = mx;
+            o[(size_t)(33 + ty) * cells + loc] = __fdiv_rn(sum, cnt);
+            o[(size_t)(37 + ty) * cells + loc] = cnt * 0.125f;
+        }
+        return;
     }
     for (int e = lane; e < ne; e += W::G) {
         const int loc = w.en()[e].loc, ty = w.en()[e].type_lv & 3;
