@@ -18,6 +18,8 @@ struct td_handle {
     int device, kind, L, cells, cells_pad, n_envs;
     int n_maps, map_stride, difficulty;
     int record_bytes, map_bytes, smem_per_warp, scratch_off;
+    int old_lists_off;
+    const float *obs_synced;       // buffer that holds the current observation of every env (NULL: none known)
     int off_static, off_towers, off_enemies, off_map6, rng_cache_words;
     uint8_t *records;
     uint8_t *maps;
@@ -198,6 +200,7 @@ static void fill_params(const td_handle *h, StepParams &p)
     p.rng_cache_words = h->rng_cache_words;
     p.difficulty = h->difficulty;
     p.opponent_seeded = h->opponent_seeded ? 1 : 0;
+    p.old_lists_off = h->old_lists_off;
 }
 
 static int grid_of(const td_handle *h) { return (h->n_envs + kWarpsPerCta - 1) / kWarpsPerCta; }
@@ -229,23 +232,26 @@ static int step_variant(int kind, bool multi)
     return kind == TD_KIND_DEF ? (multi ? 1 : 0) : kind == TD_KIND_ATK ? 2 : (multi ? 4 : 3);
 }
 
-template <int CELLS, int NCHUNK, int GW, typename F> static cudaError_t for_each_kind(F f)
+template <int CELLS, int NCHUNK, int GW, bool INC, typename F> static cudaError_t for_each_kind(F f)
 {
     cudaError_t e;
-    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
-    if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
-    if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
-    if ((e = f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK, GW>)) != cudaSuccess) return e;
-    return f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK, GW>);
+    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
+    return f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK, GW, INC>);
 }
 
-template <typename F> static cudaError_t for_each_step_kernel(const td_handle *h, F f)
+// incremental: the in-place observation update (specialised board sizes only; others always write in full)
+template <typename F> static cudaError_t for_each_step_kernel(const td_handle *h, bool incremental, F f)
 {
     switch (h->L) {
-    case 10: return for_each_kind<100, 32 / TD_GROUP_SMALL, TD_GROUP_SMALL>(f);     // 32 live enemies
-    case 20: return for_each_kind<400, 2, 32>(f);
-    case 30: return for_each_kind<900, 2, 32>(f);
-    default: return for_each_kind<0, 2, 32>(f);
+    case 10:
+        return incremental ? for_each_kind<100, 32 / TD_GROUP_SMALL, TD_GROUP_SMALL, true>(f)
+                           : for_each_kind<100, 32 / TD_GROUP_SMALL, TD_GROUP_SMALL, false>(f);   // 32 live enemies
+    case 20: return incremental ? for_each_kind<400, 2, 32, true>(f) : for_each_kind<400, 2, 32, false>(f);
+    case 30: return incremental ? for_each_kind<900, 2, 32, true>(f) : for_each_kind<900, 2, 32, false>(f);
+    default: return for_each_kind<0, 2, 32, false>(f);
     }
 }
 
@@ -282,8 +288,12 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->record_bytes = h->off_enemies + TD_CAP_ENEMIES * kEnemyBytes;
     h->scratch_off = h->record_bytes;
     int scratch = std::max(1024, std::max(h->cells_pad, round16(2 * std::min(h->cells, 6 * map_size)) + 256));   // + shuffle word buffer
-    if (env_kind != TD_KIND_2P) scratch += kTwistStageBytes;        // staging area of the opponent generator's twist
+    // slice = [record | scratch | pre-step tower / enemy cells (incremental observation) | twist staging area]
+    h->old_lists_off = h->record_bytes + scratch;
+    scratch += kOldListBytes;
+    if (env_kind != TD_KIND_2P) scratch += kTwistStageBytes;
     h->smem_per_warp = h->record_bytes + scratch;
+    h->obs_synced = nullptr;
     h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
     h->opponent_seeded = false; h->steps = 0;
     h->pipe[0] = h->pipe[1] = nullptr; h->pipe_done[0] = h->pipe_done[1] = nullptr; h->pipe_start = nullptr;
@@ -296,7 +306,8 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     size_t smem = smem_of(h);
     const size_t step_smem = step_smem_bytes(h);
     if (step_smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
-    if ((e = for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
+    if ((e = for_each_step_kernel(h, false, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
+        (e = for_each_step_kernel(h, true, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
         (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel<0>, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel<100>, smem)) != cudaSuccess ||
@@ -434,6 +445,8 @@ extern "C" int td_reset(td_handle *h, const uint8_t *mask_dev, const int32_t *ma
     fill_params(h, p);
     td_reset_kernel<<<grid_of(h), kWarpsPerCta * 32, smem_of(h), (cudaStream_t)stream>>>(p, mask_dev, map_ids_dev, obs_dev);
     TD_CUDA(h, cudaGetLastError());
+    if (!mask_dev) h->obs_synced = obs_dev;                      // every env restarted: obs_dev (if any) is current
+    else if (obs_dev != h->obs_synced) h->obs_synced = nullptr;  // some envs restarted without updating the known buffer
     return TD_OK;
 }
 
@@ -544,7 +557,13 @@ static int check_io(td_handle *h, const td_step_io *io)
 }
 
 // launch the fused step for envs [begin, begin + count) on `s`
-static int launch_step(td_handle *h, const td_step_io *io, int begin, int count, cudaStream_t s)
+// td_step_io.obs_incremental is honoured only for the buffer the library itself filled last
+static bool obs_is_current(const td_handle *h, const td_step_io *io)
+{
+    return io->obs_incremental != 0 && io->obs_dev != nullptr && io->obs_dev == h->obs_synced;
+}
+
+static int launch_step(td_handle *h, const td_step_io *io, int begin, int count, cudaStream_t s, bool incremental)
 {
     StepParams p;
     fill_params(h, p);
@@ -557,11 +576,11 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
     static const int pad_kb = getenv("TD_STEP_SMEM_KB") ? atoi(getenv("TD_STEP_SMEM_KB")) : 0;   // experiments
     if (pad_kb > 0 && (size_t)pad_kb * 1024 > smem) {
         smem = (size_t)pad_kb * 1024;
-        for_each_step_kernel(h, [&](auto kernel) { return allow_smem(kernel, smem); });
+        for_each_step_kernel(h, incremental, [&](auto kernel) { return allow_smem(kernel, smem); });
     }
     const int want = step_variant(h->kind, io->multi_action != 0);
     int seen = 0;
-    cudaError_t le = for_each_step_kernel(h, [&](auto kernel) {
+    cudaError_t le = for_each_step_kernel(h, incremental, [&](auto kernel) {
         if (seen++ == want) kernel<<<grid, block, smem, s>>>(p);
         return cudaSuccess;
     });
@@ -576,8 +595,9 @@ extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
     int rc = check_io(h, io);
     if (rc != TD_OK) return rc;
     TD_CUDA(h, cudaSetDevice(h->device));
-    rc = launch_step(h, io, 0, h->n_envs, (cudaStream_t)stream);
+    rc = launch_step(h, io, 0, h->n_envs, (cudaStream_t)stream, obs_is_current(h, io));
     if (rc != TD_OK) return rc;
+    h->obs_synced = io->obs_dev;
     h->steps += h->n_envs;
     return TD_OK;
 }
@@ -603,6 +623,7 @@ extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
     case 30: td_observe_kernel<900><<<grid, block, smem, s>>>(p, obs_dev); break;
     default: td_observe_kernel<0><<<grid, block, smem, s>>>(p, obs_dev); break;
     }
+    h->obs_synced = obs_dev;
     TD_CUDA(h, cudaGetLastError());
     return TD_OK;
 }
@@ -638,6 +659,7 @@ extern "C" int td_observe_snapshot(td_handle *h, const void *records_dev, int n,
     case 30: td_observe_kernel<900><<<grid, block, smem, s>>>(p, obs_dev); break;
     default: td_observe_kernel<0><<<grid, block, smem, s>>>(p, obs_dev); break;
     }
+    if (obs_dev == h->obs_synced) h->obs_synced = nullptr;      // the buffer now shows the snapshot, not the live envs
     TD_CUDA(h, cudaGetLastError());
     return TD_OK;
 }
@@ -672,6 +694,8 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
         for (int k = 0; k < 2; ++k) TD_CUDA(h, cudaStreamWaitEvent(h->pipe[k], h->pipe_start, 0));
     }
     const int base = h->n_envs / chunks, rem = h->n_envs % chunks;
+    const bool incremental = obs_is_current(h, io);
+    h->obs_synced = nullptr;                                    // until every chunk was launched
     int begin = 0;
     for (int c = 0; c < chunks; ++c) {
         const int count = base + (c < rem ? 1 : 0);
@@ -685,7 +709,7 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
                                        n * atk_w * 8, cudaMemcpyHostToDevice, st));
         if (io->opponent_dev && host->opponent_host)
             TD_CUDA(h, cudaMemcpyAsync((uint8_t *)io->opponent_dev + b, host->opponent_host + b, n, cudaMemcpyHostToDevice, st));
-        rc = launch_step(h, io, begin, count, st);
+        rc = launch_step(h, io, begin, count, st, incremental);
         if (rc != TD_OK) return rc;
         // device -> host for this chunk: outputs that sit at matching offsets of one device slab and one host
         // slab (as TDVecEnv allocates them) are merged into a single copy when the chunk is the whole batch
@@ -726,6 +750,7 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
             TD_CUDA(h, cudaStreamWaitEvent(s, h->pipe_done[k], 0));
         }
     }
+    h->obs_synced = io->obs_dev;
     h->steps += h->n_envs;
     TD_CUDA(h, cudaStreamSynchronize(s));
     return TD_OK;
@@ -744,6 +769,7 @@ extern "C" int td_get_state(td_handle *h, int first_env, int n, void *blob)
 extern "C" int td_set_state(td_handle *h, int first_env, int n, const void *blob)
 {
     if (!h) return TD_E_INVALID;
+    h->obs_synced = nullptr;                                    // no buffer shows the state being written
     if (!blob || first_env < 0 || n < 1 || first_env + n > h->n_envs) return fail(h, TD_E_INVALID, "td_set_state: bad range");
     const uint8_t *b = static_cast<const uint8_t *>(blob);
     for (int i = 0; i < n; ++i) {

@@ -46,7 +46,8 @@ class TdStepIO(C.Structure):
                 ("multi_action", C.c_int32), ("auto_reset", C.c_int32),
                 ("obs_dev", C.c_void_p), ("reward_dev", C.c_void_p), ("done_dev", C.c_void_p),
                 ("win_dev", C.c_void_p), ("allow_next_dev", C.c_void_p), ("real_def_dev", C.c_void_p),
-                ("real_atk_dev", C.c_void_p), ("fail_def_dev", C.c_void_p), ("fail_atk_dev", C.c_void_p)]
+                ("real_atk_dev", C.c_void_p), ("fail_def_dev", C.c_void_p), ("fail_atk_dev", C.c_void_p),
+                ("obs_incremental", C.c_int32), ("reserved_", C.c_int32)]
 
 
 class TdHostIO(C.Structure):
@@ -132,7 +133,7 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.td_gae.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                              C.c_void_p, C.c_void_p, C.c_void_p]
-        if L.td_abi_version() != 1:
+        if L.td_abi_version() != 2:
             raise ImportError("libtd_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -268,8 +269,9 @@ class Engine(object):
     @staticmethod
     def make_io(def_action=None, atk_action=None, opponent=None, multi_action=False, auto_reset=False, obs=None,
                 reward=None, done=None, win=None, allow_next=None, real_def=None, real_atk=None, fail_def=None,
-                fail_atk=None):
+                fail_atk=None, obs_incremental=False):
         io = TdStepIO()
+        io.obs_incremental = int(bool(obs_incremental))
         io.def_action_dev, io.atk_action_dev, io.opponent_dev = _ptr(def_action), _ptr(atk_action), _ptr(opponent)
         io.multi_action, io.auto_reset = int(bool(multi_action)), int(bool(auto_reset))
         io.obs_dev, io.reward_dev, io.done_dev, io.win_dev = _ptr(obs), _ptr(reward), _ptr(done), _ptr(win)

@@ -57,12 +57,17 @@ class _Info(dict):
 
 class TDVecEnv(object):
     def __init__(self, kind, map_size, num_envs, seed=0, device=0, difficulty=1, auto_reset=True, env_offset=0,
-                 n_maps=None, scripted_opponent=True, multi_action=None, cfg=None, mapgen_threads=None):
+                 n_maps=None, scripted_opponent=True, multi_action=None, cfg=None, mapgen_threads=None,
+                 incremental_obs=False):
         if kind not in E.KINDS:
             raise ValueError("kind must be one of %r" % (sorted(E.KINDS),))
         self.kind, self.map_size, self.num_envs = kind, int(map_size), int(num_envs)
         self.device = torch.device("cuda", device)
         self.auto_reset = bool(auto_reset)
+        # incremental_obs: `self.obs` is only ever written by this env, so the step may update it in place instead
+        # of rewriting all 45 planes (td_step_io.obs_incremental; the tensor is bit-identical either way).  Leave
+        # it off if you write into `env.obs` yourself.
+        self.incremental_obs = bool(incremental_obs)
         self.multi_action = params.hyper_parameters.allow_multiple_actions if multi_action is None else bool(multi_action)
         if kind == "atk":
             self.multi_action = False
@@ -144,6 +149,7 @@ class TDVecEnv(object):
                 done=self._done, win=self.win, allow_next=self._allow, real_def=self.real_def,
                 real_atk=self.real_atk, fail_def=self.fail_def, fail_atk=self.fail_atk)
         io.auto_reset = int(self.auto_reset)
+        io.obs_incremental = int(self.incremental_obs)
         io.obs_dev = E._ptr(self.obs)
         io.def_action_dev = d.data_ptr() if d is not None else None
         io.atk_action_dev = a.data_ptr() if a is not None else None

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 1
+#define TD_ABI_VERSION 2
 
 enum { TD_OK = 0, TD_E_INVALID = -1, TD_E_CUDA = -2, TD_E_ALLOC = -3, TD_E_STATE = -4,
        TD_E_OVERFLOW = -5 };
@@ -122,6 +122,17 @@ typedef struct td_step_io {
     int64_t *real_atk_dev;           /* [n,3,8] */
     int32_t *fail_def_dev;           /* [n] */
     int32_t *fail_atk_dev;           /* [n,4]: count, then up to 3 codes (FailCode list of TDAttack/TDMulti) */
+    /* options */
+    int32_t obs_incremental;         /* != 0: obs_dev is the buffer this handle wrote its previous observation to
+                                        (td_reset / td_observe / the last td_step) and nobody changed it since: the
+                                        step then rewrites only what changed -- the planes that carry per-step
+                                        scalars, the buildable plane, the old and new tower / enemy cells -- and
+                                        leaves the static map planes and the untouched zeros alone.  The resulting
+                                        tensor is bit-identical to a full write.  Ignored (full write) whenever the
+                                        library cannot vouch for the buffer: another pointer than last time, after
+                                        td_set_state, for envs that were reset inside the step, for board sizes
+                                        without a specialised kernel. */
+    int32_t reserved_;
 } td_step_io;
 
 /* byte offsets inside one env record, for td_get_state / td_set_state blobs */

@@ -144,7 +144,7 @@ def compare_state(tag, eng, rec, o):
 
 
 def run_parity(kind, L, n_envs, steps, seed=0, multi=False, opponent="device", difficulty=1, cfg_overrides=None,
-               check_state_every=1, device=0, use_host_api=False, multi_mode="sparse"):
+               check_state_every=1, device=0, use_host_api=False, multi_mode="sparse", incremental=False):
     """Step `n_envs` instances on the GPU and in the oracle; compare everything each step.
 
     opponent: "device" (on-device CPython-compatible generator), "stream" (host-resolved type/road
@@ -220,7 +220,8 @@ def run_parity(kind, L, n_envs, steps, seed=0, multi=False, opponent="device", d
                               opponent=opp if (kind == "def" and opponent == "stream") else None,
                               multi_action=multi, auto_reset=False, obs=obs, reward=t["reward"], done=t["done"],
                               win=t["win"], allow_next=t["allow_next"], real_def=t["real_def"],
-                              real_atk=t["real_atk"], fail_def=t["fail_def"], fail_atk=t["fail_atk"])
+                              real_atk=t["real_atk"], fail_def=t["fail_def"], fail_atk=t["fail_atk"],
+                              obs_incremental=incremental)
         # snapshot the records of finished envs: they must not be stepped in the comparison below
         eng.step(io, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()

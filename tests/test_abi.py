@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), "libtd_b200.so lacks %s" % n
     assert sorted(E.EXPORTS) == names
-    assert lib.td_abi_version() == 1
+    assert lib.td_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -87,3 +87,45 @@ def test_unusual_board_sizes_and_batch_sizes(L, n):
     """The run-time-size kernel variant ('TD-def-v0' with a map_size kwarg), batches that do not fill a CTA."""
     assert PU.run_parity("def", L, n_envs=n, steps=250, seed=50 + L, opponent="device") > 100
     assert PU.run_parity("2p", L, n_envs=n, steps=120, seed=60 + L, opponent="none", multi=True) > 50
+
+
+@pytest.mark.parametrize("kind,L,multi", [("def", 10, False), ("atk", 10, False), ("2p", 10, False), ("def", 20, True),
+                                          ("atk", 20, False), ("2p", 30, False)])
+def test_incremental_observation_equals_the_oracle(kind, L, multi):
+    """td_step_io.obs_incremental: the observation updated in place (changed planes, old and new tower / enemy
+    cells) must be the tensor the oracle builds from scratch, every step."""
+    assert PU.run_parity(kind, L, n_envs=16, steps=500, seed=90 + L, multi=multi,
+                         opponent="none" if kind == "2p" else "device", incremental=True) > 1500
+
+
+def test_incremental_observation_with_auto_reset_and_buffer_changes():
+    """Two batched envs, one writing full observations and one updating in place, stay bit-identical through
+    auto-resets; the library falls back to a full write when it cannot vouch for the buffer."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    for kind, L in (("def", 10), ("atk", 10), ("2p", 20)):
+        N = 2048
+        full = TDVecEnv(kind, L, N, seed=5, auto_reset=True)
+        inc = TDVecEnv(kind, L, N, seed=5, auto_reset=True, incremental_obs=True)
+        assert torch.equal(full.reset(), inc.reset())
+        g = torch.Generator(device="cuda").manual_seed(3)
+        resets = 0
+        for k in range(260):
+            d = torch.randint(0, 6 * L * L + 1, (N,), dtype=torch.int64, device="cuda", generator=g)
+            a = torch.randint(0, 5, (N, 3, 8), dtype=torch.int64, device="cuda", generator=g)
+            act = d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+            o1, r1, d1, _ = full.step(act)
+            if k == 100:
+                inc.obs.fill_(7.0)                          # someone scribbled over the buffer ...
+                inc.engine.observe(inc.obs)                 # ... and asked for the current observation again
+            if k == 150:
+                torch.cuda.synchronize()
+                inc.engine.set_state_raw(inc.engine.get_state_raw())   # td_set_state: the buffer is not vouched for
+                inc.obs.zero_()
+            o2, r2, d2, _ = inc.step(act)
+            assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)), (kind, k)
+            assert torch.equal(r1, r2) and torch.equal(d1, d2)
+            resets += int(d1.sum().item())
+        assert resets > 0                                      # auto-resets happened inside the comparison
+        full.close()
+        inc.close()
