@@ -56,7 +56,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    env = G.make_vec(args.env, args.envs, seed=0, device=local, env_offset=rank * 1_000_000)
+    # the policy reads env.obs in place and nothing else writes it: let the step update it incrementally
+    env = G.make_vec(args.env, args.envs, seed=0, device=local, env_offset=rank * 1_000_000, incremental_obs=True)
     L, kind = env.map_size, env.kind
     policy = TinyPolicy(L).cuda(local).to(memory_format=torch.channels_last).eval()
     buf = RolloutBuffer(env, horizon=args.horizon) if kind in ("def", "atk") else None
