@@ -193,6 +193,19 @@ template <class W> __device__ __forceinline__ bool gall(const W &w, bool pred) {
 template <class W> __device__ __forceinline__ bool gany(const W &w, bool pred) { return __any_sync(w.gmask, pred); }
 template <class W> __device__ __forceinline__ void gsync(const W &w) { __syncwarp(w.gmask); }
 
+// n16 <= MAXN int4 with a compile-time bound: one predicated load/store pair per pass instead of a loop.
+template <int MAXN, int G>
+__device__ __forceinline__ void copy16_upto(void *dst, const void *src, int n16, int lane)
+{
+    int4 *d = reinterpret_cast<int4 *>(dst);
+    const int4 *s = reinterpret_cast<const int4 *>(src);
+#pragma unroll
+    for (int k = 0; k < (MAXN + G - 1) / G; ++k) {
+        const int q = lane + G * k;
+        if (q < n16) d[q] = s[q];
+    }
+}
+
 __device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16, int lane, int stride)
 {
     int4 *d = reinterpret_cast<int4 *>(dst);
@@ -391,15 +404,29 @@ __device__ __forceinline__ void load_env(W &w, const StepParams &p, const uint8_
 }
 
 // Write back the header block (incl. the word cache), the changed maps and the live list prefixes.
-template <class W>
+// UNROLLED: predicated single-pass copies instead of loops -- 45 fewer instructions per env-step.  Measured on
+// B200: attacker env 0.291 -> 0.273 ms, in-place observation update (def-small) 0.191 -> 0.167 ms, but the
+// full-write defender step 0.2175 -> 0.2220 ms (same box, twice), so the caller chooses per kernel variant.
+template <bool UNROLLED = false, class W>
 __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *rec, bool map6_dirty, bool push = true)
 {
     if (push) push_header(w);
     gsync(w);
     const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : w.hdr_bytes());
-    warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
-    warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane, W::G);
-    warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane, W::G);
+    if (!UNROLLED) {
+        warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
+        warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane, W::G);
+        warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane, W::G);
+        return;
+    }
+    if (W::kCells > 0 && W::kRngWords > 0) {
+        constexpr int kHeadMax = (kOffRngCache + 4 * W::kRngWords + 3 * W::kPad + kMapHdrBytes) / 16;   // = off_towers / 16
+        copy16_upto<kHeadMax, W::G>(rec, w.slice, head >> 4, w.lane);
+    } else {
+        warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
+    }
+    copy16_upto<TD_CAP_TOWERS, W::G>(rec + w.off_towers(), w.tw(), w.nt, w.lane);
+    copy16_upto<(TD_CAP_ENEMIES * 3 + 1) / 2, W::G>(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane);
 }
 
 // TDGymBasic.reset (:37-55) + TDBoard.__init__ (:63-79): fresh episode on map `map_id`.
@@ -1612,7 +1639,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");          // the next step's generator words are in the slice
-    store_env(w, p, rec, dirty, false);
+    store_env<(INC || KIND == TD_KIND_ATK)>(w, p, rec, dirty, false);
 }
 
 // reset (mask / explicit map ids) and observation-only kernels
