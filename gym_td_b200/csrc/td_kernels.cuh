@@ -1,11 +1,13 @@
 // td_kernels.cuh -- sm_100a kernels for the batched gym-TD board step.
 //
 // One warp advances one game instance.  The env record (header, tower list, enemy list, map6)
-// is staged from HBM into the warp's private shared-memory slice with 16-byte coalesced loads,
-// all game rules run warp-cooperatively on that slice (lanes = towers or enemies, ballots and
-// shuffles instead of loops where the reference loops), the (45, L, L) float32 observation is
-// written with streaming 128-bit stores, and the live prefix of the record is written back.
-// No block-level synchronisation exists anywhere: warps never communicate.
+// is staged from HBM into the warp's private shared-memory slice with asynchronous 16-byte copies
+// (cp.async, one round trip), all game rules run warp-cooperatively on that slice (lanes = towers
+// or enemies, ballots, matches and shuffles instead of loops where the reference loops), the
+// (45, L, L) float32 observation is written with unrolled 128-bit stores (or updated in place,
+// INC kernels), and the live prefix of the record is written back.  Nothing stays in registers
+// across the observation stores.  No block-level synchronisation exists anywhere: warps never
+// communicate.  DESIGN.md section 7 lists what was measured to get here, including the dead ends.
 //
 // Reference semantics followed (file:line under gym_TD/envs/):
 //   (a) defender decode + build/LvUp/destruct  TDDefense.py:38-77, TDMulti.py:65-115, TDBoard.py:226-293,
