@@ -35,6 +35,42 @@ def test_struct_sizes_match_header():
     assert E.HEADER_DTYPE.itemsize == 64
 
 
+def test_ctypes_mirrors_have_the_headers_layout(tmp_path):
+    """Size and every field offset of the ctypes structures, against what gcc sees in include/td_b200.h."""
+    import subprocess
+    pairs = {"td_config": E.TdConfig, "td_map": E.TdMap, "td_step_io": E.TdStepIO, "td_host_io": E.TdHostIO,
+             "td_layout": E.TdLayout, "td_stats": E.TdStats}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "td_b200.h"', 'int main(void) {']
+    for cname, cls in pairs.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    records = {"td_env_header": E.HEADER_DTYPE, "td_tower_rec": E.TOWER_DTYPE, "td_enemy_rec": E.ENEMY_DTYPE}
+    for cname, dt in records.items():
+        lines.append('printf("%s size %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname in dt.names:
+            lines.append('printf("%s %s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = {}
+    for ln in subprocess.check_output([str(exe)], text=True).splitlines():
+        struct, field, value = ln.split()
+        got[(struct, field)] = int(value)
+    for cname, cls in pairs.items():
+        assert got[(cname, "size")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+    for cname, dt in records.items():                       # the numpy views of td_get_state blobs
+        for fname in dt.names:
+            assert got[(cname, fname)] == dt.fields[fname][1], (cname, fname)
+    assert got[("td_env_header", "size")] == E.HEADER_DTYPE.itemsize == 64
+    assert got[("td_tower_rec", "size")] == E.TOWER_DTYPE.itemsize == 16
+    assert got[("td_enemy_rec", "size")] == E.ENEMY_DTYPE.itemsize == 24
+
+
 def test_default_config_equals_reference_values():
     c = E.config_struct(params.Config())
     assert [list(r) for r in c.enemy_LP] == [[820, 1700], [2050, 3000], [6000, 8000], [8000, 12000]]
