@@ -104,3 +104,25 @@ def test_no_cpu_fallback():
     import gym_td_b200
     with pytest.raises(E.TdError):
         gym_td_b200.make("TD-def-small-v0", seed=1)
+
+
+def test_plain_c_program_against_the_library(tmp_path):
+    """examples/c_abi_demo.c: the boundary used from C alone.  Host-only entry points work everywhere; td_create
+    reports TD_E_CUDA with a message on a box without a GPU (exit code 3) and the demo runs through on one."""
+    import subprocess
+    E.lib()                                                   # builds the library if needed
+    cuda = "/usr/local/cuda"
+    if not os.path.isdir(os.path.join(cuda, "include")):
+        pytest.skip("CUDA toolkit headers not found")
+    exe = tmp_path / "c_abi_demo"
+    libdir = os.path.join(ROOT, "gym_td_b200")
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"), "-o", str(exe),
+                           os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-ltd_b200",
+                           "-Wl,-rpath," + libdir, "-L", os.path.join(cuda, "lib64"), "-lcudart"])
+    res = subprocess.run([str(exe), "256", "20"], capture_output=True, text=True, timeout=300)
+    assert "ABI version 2" in res.stdout and "road(s)" in res.stdout
+    assert res.returncode in (0, 3), res.stdout + res.stderr
+    if res.returncode == 3:
+        assert "no CPU fallback" in res.stdout
+    else:
+        assert "env-steps" in res.stdout
