@@ -236,10 +236,24 @@ def survey_kats():
     json.dump(kats, open(os.path.join(OUT, "survey_kats.json"), "w"), indent=1)
 
 
+def extra():
+    """Second batch of recorded trajectories (python oracle/make_golden.py --extra): the first batch stays as it is."""
+    record("atk", 10, 510, 600, difficulty=2)
+    record("atk", 30, 550, 300, difficulty=2)
+    record("def", 20, 540, 400, difficulty=0)
+    record("def", 30, 520, 200, multi=True)
+    record("2p", 30, 530, 200, multi=True)
+    record("atk", 20, 560, 600, overrides=dict(enemy_upgrade_at=0.05, max_cost=150, reward_kill=0.25),
+           tag="atk_L20_override_c")
+
+
 def main():
     ref_loader.load()
     np.seterr(all="ignore")
     os.makedirs(OUT, exist_ok=True)
+    if "--extra" in sys.argv:
+        extra()
+        return 0
     reference_selftest()
     survey_kats()
     golden_maps()
