@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 2
+#define TD_ABI_VERSION 2   /* 2: td_step_io grew `obs_incremental` (+ reserved_) at its end */
 
 enum { TD_OK = 0, TD_E_INVALID = -1, TD_E_CUDA = -2, TD_E_ALLOC = -3, TD_E_STATE = -4,
        TD_E_OVERFLOW = -5 };
