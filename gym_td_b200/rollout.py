@@ -5,7 +5,6 @@ Replaces the host-side bookkeeping of train/main.py:79-176 and train/PPO/{Callba
 behind the C ABI (td_rollout_mask / td_rollout_record / td_gae).  Buffers are [horizon, n] torch tensors in HBM,
 env index fastest; observations are not copied (the learner reads `env.obs` in place, or rebuilds them).
 """
-import ctypes as C
 
 import torch
 

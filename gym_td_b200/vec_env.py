@@ -11,7 +11,6 @@ map seed >= seed + g (numpy RandomState stream, num_roads drawn first) and a scr
 generator in the state of CPython's random.seed(seed + g), which keeps running across episodes
 like the reference's global `random` module does.
 """
-import ctypes as C
 
 import numpy as np
 import torch
