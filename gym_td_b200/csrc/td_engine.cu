@@ -31,6 +31,7 @@ struct td_handle {
     cudaStream_t pipe[2];          // internal streams of the chunked host path (td_step_host)
     cudaEvent_t pipe_done[2], pipe_start;
     td_config cfg;
+    DevConfig dev_cfg;             // derived tables of cfg; copied into the parameters of every launch (per handle)
     std::string err;
 };
 
@@ -119,9 +120,11 @@ static int validate_config(td_handle *h, const td_config *c)
     return TD_OK;
 }
 
-static int upload_config(td_handle *h, const td_config *c)
+// td_config -> the derived tables the kernels read.  The result lives in the handle and rides in the kernel
+// parameters of every launch, so handles with different configs coexist on one device.
+static int derive_config(td_handle *h, const td_config *c)
 {
-    DevConfig d;
+    DevConfig &d = h->dev_cfg;
     memset(&d, 0, sizeof(d));
     for (int t = 0; t < TD_NTYPES; ++t)
         for (int l = 0; l < TD_NLV; ++l) {
@@ -172,7 +175,6 @@ static int upload_config(td_handle *h, const td_config *c)
     d.atk_interval = c->attacker_action_interval;
     d.def_interval = c->defender_action_interval;
     d.max_steps = c->max_episode_steps;
-    TD_CUDA(h, cudaMemcpyToSymbol(cc, &d, sizeof(d)));
     h->cfg = *c;
     return TD_OK;
 }
@@ -201,6 +203,7 @@ static void fill_params(const td_handle *h, StepParams &p)
     p.difficulty = h->difficulty;
     p.opponent_seeded = h->opponent_seeded ? 1 : 0;
     p.old_lists_off = h->old_lists_off;
+    p.cfg = h->dev_cfg;
 }
 
 static int grid_of(const td_handle *h) { return (h->n_envs + kWarpsPerCta - 1) / kWarpsPerCta; }
@@ -325,7 +328,7 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
         h->err = std::string("device allocation failed: ") + cudaGetErrorString(e);
         return bail(TD_E_ALLOC);
     }
-    rc = upload_config(h, cfg);
+    rc = derive_config(h, cfg);
     if (rc != TD_OK) return bail(rc);
     *out = h;
     return TD_OK;
@@ -353,9 +356,7 @@ extern "C" int td_set_config(td_handle *h, const td_config *cfg)
     if (!h) return TD_E_INVALID;
     int rc = validate_config(h, cfg);
     if (rc != TD_OK) return rc;
-    TD_CUDA(h, cudaSetDevice(h->device));
-    TD_CUDA(h, cudaDeviceSynchronize());
-    return upload_config(h, cfg);
+    return derive_config(h, cfg);       // takes effect with the next launch; kernels in flight keep their copy
 }
 
 extern "C" int td_get_layout(const td_handle *h, td_layout *out)

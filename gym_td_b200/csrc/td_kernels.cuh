@@ -90,8 +90,6 @@ struct DevConfig {
     double min_enemy_cost[TD_NLV];   // cheapest enemy type per level: below it every remaining cluster slot fails
 };
 
-__constant__ DevConfig cc;
-
 struct MapHdr {            // 16 bytes, head of a map-pool record
     uint16_t start[3];
     uint16_t end;
@@ -118,6 +116,7 @@ struct StepParams {
     int opponent_seeded;
     int old_lists_off;         // offset of the pre-step tower / enemy cell lists inside a slice
     td_step_io io;
+    DevConfig cfg;             // per handle: travels with every launch in the kernel-parameter constant bank
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -435,6 +434,7 @@ __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *re
 template <class W>
 __device__ __forceinline__ void reset_env(W &w, const StepParams &p, int map_id, bool reload_map)
 {
+    const DevConfig &cc = w.pp->cfg;
     if (reload_map) {
         gsync(w);
         load_static_map(w, p, map_id);
@@ -527,10 +527,10 @@ __device__ __forceinline__ double py_random(W &w)
 
 // map[6] += delta on the Manhattan diamond around `loc` (TDBoard.py:239-245, 281-287).  Out of line: it is
 // reached from several build / destruct sites and only on the rare successful operation.
-__device__ __noinline__ void diamond_add_cells(uint8_t *map6, int loc, int delta, int L, int lane, int stride,
+__device__ __noinline__ void diamond_add_cells(uint8_t *map6, int loc, int delta, int L, int D, int lane, int stride,
                                                unsigned gmask)
 {
-    const int D = cc.tower_distance, WD = 2 * D + 1;
+    const int WD = 2 * D + 1;
     const int r0 = loc / L, c0 = loc - r0 * L;
     for (int k = lane; k < WD * WD; k += stride) {
         int i = k / WD - D, j = k % WD - D;
@@ -544,12 +544,13 @@ __device__ __noinline__ void diamond_add_cells(uint8_t *map6, int loc, int delta
 template <class W>
 __device__ __forceinline__ void diamond_add(W &w, int loc, int delta)
 {
-    diamond_add_cells(w.map6(), loc, delta, w.L(), w.lane, W::G, w.gmask);
+    diamond_add_cells(w.map6(), loc, delta, w.L(), w.pp->cfg.tower_distance, w.lane, W::G, w.gmask);
 }
 
 template <class W>
 __device__ __forceinline__ bool tower_build(W &w, int t, int loc, bool &map6_dirty)   // TDBoard.py:226-247
 {
+    const DevConfig &cc = w.pp->cfg;
     const double cost = cc.tower_cost[t][0];
     if (w.cost_def < cost) { w.fail = TD_FC_COST_SHORTAGE; return false; }
     if (w.map6()[loc] > 0) { w.fail = TD_FC_INVALID_POSITION; return false; }
@@ -584,6 +585,7 @@ __device__ __forceinline__ int find_tower(const W &w, int loc)
 template <class W>
 __device__ __forceinline__ bool tower_lvup(W &w, int loc)                              // TDBoard.py:249-271
 {
+    const DevConfig &cc = w.pp->cfg;
     int idx = find_tower(w, loc);
     if (idx < 0) { w.fail = TD_FC_UNKNOWN_TARGET; return false; }
     int tl = w.tw()[idx].type_lv, ty = tl & 3, lv = tl >> 2;
@@ -601,6 +603,7 @@ __device__ __forceinline__ bool tower_lvup(W &w, int loc)                       
 template <class W>
 __device__ __forceinline__ bool tower_destruct(W &w, int loc, bool &map6_dirty)        // TDBoard.py:273-293
 {
+    const DevConfig &cc = w.pp->cfg;
     int idx = find_tower(w, loc);
     if (idx < 0) { w.fail = TD_FC_UNKNOWN_TARGET; return false; }
     int tl = w.tw()[idx].type_lv;
@@ -632,6 +635,7 @@ __device__ __forceinline__ bool tower_destruct(W &w, int loc, bool &map6_dirty) 
 template <class W>
 __device__ __forceinline__ bool decode_discrete(W &w, long long a, long long &real, int &failcode, bool &dirty)
 {
+    const DevConfig &cc = w.pp->cfg;
     const long long nop = 6ll * w.ncells();
     real = nop;
     failcode = 0;
@@ -655,6 +659,7 @@ __device__ __forceinline__ bool decode_discrete(W &w, long long a, long long &re
 template <class W>
 __device__ __forceinline__ void decode_multi(W &w, const long long *act, long long *real, bool &dirty)
 {
+    const DevConfig &cc = w.pp->cfg;
     const int cells = w.ncells();
     uint8_t *tower_at = w.scratch();      // cells bytes: 1 where a tower stands (scratch >= cells_pad here)
     const bool enabled = w.def_cd == 0;
@@ -717,6 +722,7 @@ __device__ __forceinline__ void decode_multi(W &w, const long long *act, long lo
 template <class W>
 __device__ __forceinline__ void append_enemy(W &w, int t, int lv, int start)
 {
+    const DevConfig &cc = w.pp->cfg;
     if (w.ne >= w.ecap) { w.flags |= 1; return; }
     if (w.lane == 0) {
         td_enemy_rec &e = w.en()[w.ne];
@@ -736,6 +742,7 @@ __device__ __forceinline__ void append_enemy(W &w, int t, int lv, int start)
 template <class W>
 __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, int lane_base)
 {
+    const DevConfig &cc = w.pp->cfg;
     const int start = w.mh()->start[road];
     const int lv = w.steps >= cc.upgrade_step ? 1 : 0;      // progress >= enemy_upgrade_at
     const int tv = (mine < 0 || mine >= TD_NTYPES) ? TD_NTYPES : (int)mine;     // 4 == enemy_types: empty slot
@@ -782,6 +789,7 @@ __device__ __forceinline__ bool summon_cluster(W &w, int road, long long &mine, 
 template <class W>
 __device__ __forceinline__ void summon_uniform(W &w, int t, int road)
 {
+    const DevConfig &cc = w.pp->cfg;
     const int start = w.mh()->start[road];
     const int lv = w.steps >= cc.upgrade_step ? 1 : 0;      // progress >= enemy_upgrade_at
     const double cost = cc.enemy_cost[t][lv];
@@ -812,6 +820,7 @@ __device__ __forceinline__ void summon_uniform(W &w, int t, int road)
 template <class W>
 __device__ __forceinline__ void opponent_enemy(W &w, int difficulty)
 {
+    const DevConfig &cc = w.pp->cfg;
     if (w.atk_cd != 0) return;
     if (difficulty == 0) {                                   // random_enemy_lv0
         long long mine = 0;
@@ -829,6 +838,7 @@ __device__ __forceinline__ void opponent_enemy(W &w, int difficulty)
 template <class W>
 __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty)
 {
+    const DevConfig &cc = w.pp->cfg;
     if (w.def_cd != 0) return;
     const int L = w.L();
     if (difficulty == 0) {                                   // random_tower_lv0
@@ -911,6 +921,7 @@ struct EnemyRegs {
 template <int NCHUNK, class W>
 __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_out)
 {
+    const DevConfig &cc = w.pp->cfg;
     const int L = w.L(), lane = w.lane;
     double reward = __dadd_rn(0.0, cc.reward_time);
     w.steps += 1;
@@ -1156,6 +1167,7 @@ __device__ __forceinline__ void store_run(float4 *p, float v, int lane)
 template <class W>
 __device__ __forceinline__ void obs_prepare(W &w)
 {
+    const DevConfig &cc = w.pp->cfg;
     const int lane = w.lane;
     // The 12 broadcast values (f64 quotients rounded once to f32, TDBoard.py:115-125,134-142), one per lane:
     // lane 0 -> plane 5, 1 -> 11, 2 -> 12, 3 -> 13, 4..7 -> 41..44 (cost_def / enemy_cost / 8), 8..11 -> 21..24.
@@ -1296,6 +1308,7 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
 template <class W>
 __device__ __forceinline__ void obs_sparse(W &w, float *o)
 {
+    const DevConfig &cc = w.pp->cfg;
     constexpr int CELLS = W::kCells;
     const int lane = w.lane, cells = CELLS > 0 ? CELLS : w.ncells();
     // ---- enemy statistics per (type, cell) group in list order, float32 (TDBoard.py:355-365, NumPy-2 casts)
@@ -1449,6 +1462,7 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 template <int KIND, bool MULTI, int NCHUNK, bool INC, class W>
 __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W &w, uint8_t *rec, bool &dirty)
 {
+    const DevConfig &cc = p.cfg;
     constexpr int GW = W::G;
     const int lane = w.lane;
     const td_step_io &io = p.io;
@@ -1618,7 +1632,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
 // INC: the observation is an in-place update of the previous one (td_step_io.obs_incremental, vouched for by the
 // engine); a separate instantiation, so that the full-write kernels carry none of its code.
 template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const StepParams p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
@@ -1659,7 +1673,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kern
 
 // reset (mask / explicit map ids) and observation-only kernels
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids, float *obs)
+td_reset_kernel(const __grid_constant__ StepParams p, const uint8_t *mask, const int32_t *map_ids, float *obs)
 {
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;
@@ -1680,7 +1694,7 @@ td_reset_kernel(const StepParams p, const uint8_t *mask, const int32_t *map_ids,
 }
 
 template <int CELLS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const StepParams p, float *obs)
+__global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const __grid_constant__ StepParams p, float *obs)
 {
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;

@@ -78,7 +78,9 @@ class TDVecEnv(object):
         self.engine.upload_maps(maps)
         self.engine.set_map_stride(1)
         self.num_roads = np.array([maps[i].num_roads for i in range(n_maps)], dtype=np.int32)
-        if scripted_opponent and kind != "2p":
+        self.scripted = bool(scripted_opponent and kind != "2p")
+        self.difficulty = int(difficulty)
+        if self.scripted:
             self.engine.set_difficulty(difficulty)
             self.engine.seed_opponent_python((np.arange(num_envs, dtype=np.uint64) + base).astype(np.uint32))
         N, L, dev = self.num_envs, self.map_size, self.device
