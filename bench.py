@@ -46,6 +46,11 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--repeats", type=int, default=5, help="timed segments of --steps steps each; the median is reported")
+    ap.add_argument("--replay", type=int, default=64, help="envs per rank replayed through the CPU oracle after timing (0 = off)")
+    ap.add_argument("--replay-steps", type=int, default=100)
+    ap.add_argument("--no-side-workloads", action="store_true", help="skip BASELINE configs 3-5 (atk-small, def-middle-multi, 2p-large)")
+    ap.add_argument("--side-workloads-multi", action="store_true", help="run the side workloads under torchrun too")
     return ap.parse_args()
 
 
@@ -201,6 +206,152 @@ def emit(line):
         os.write(_REAL_STDOUT, data)
 
 
+def pin_rank_to_cores(local, local_world):
+    """One slice of the host's cores per rank, so that eight Python processes do not migrate over each other
+    (td_step_host is bound by launch + sync latency on the host side)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        per = len(cores) // max(local_world, 1)
+        if local_world > 1 and per >= 1:
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+            return per
+    except (AttributeError, OSError):
+        pass
+    return None
+
+
+def make_actions(torch, name, kind, L, n_envs, multi, dev, seed):
+    """Pre-generated synthetic actions, resident in HBM (excluded from every timed region)."""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    A = 16
+    def_pool = atk_pool = None
+    if kind != "atk":
+        if multi:
+            if name.endswith("sparse"):              # SURVEY 8(d) config 3, second variant: each flag 1 with p = 0.01
+                def_pool = (torch.rand((4, n_envs, 6, L, L), device=dev, generator=g) < 0.01).to(torch.int64)
+            else:                                    # action_space.sample(): uniform {0, 1, 2}
+                def_pool = torch.randint(0, 3, (4, n_envs, 6, L, L), dtype=torch.int64, device=dev, generator=g)
+        else:
+            def_pool = torch.randint(0, 6 * L * L + 1, (A, n_envs), dtype=torch.int64, device=dev, generator=g)
+    if kind != "def":
+        atk_pool = torch.randint(0, 5, (A, n_envs, 3, 8), dtype=torch.int64, device=dev, generator=g)
+
+    def action(k):
+        d = def_pool[k % def_pool.shape[0]] if def_pool is not None else None
+        a = atk_pool[k % atk_pool.shape[0]] if atk_pool is not None else None
+        return d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+
+    return action, def_pool, atk_pool
+
+
+def timed_repeats(torch, dist, env, action, steps, repeats, world, dev, on_first=None):
+    """`repeats` timed segments of exactly `steps` steps each, CUDA events on the launching stream, barrier +
+    synchronize on both sides of every segment, max over ranks per segment.  Returns the list of ms."""
+    out = []
+    for r in range(repeats):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if r == 0 and on_first is not None:
+            on_first()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for k in range(steps):
+            env.step(action(k))
+        end.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([start.elapsed_time(end)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out.append(float(t.item()))
+    return out
+
+
+def replay_check(torch, dist, env, action, n_sub, n_steps, world, dev):
+    """Parity inside the benchmark run: restart the batch, step it at full size and replay the first n_sub envs of
+    THIS rank through the CPU oracle (oracle/replay.py -- the checker, never the thing measured), every output
+    and the whole observation bit for bit.  Counts are summed over ranks."""
+    from oracle.replay import Replayer
+    env.incremental_obs = False
+    env.reset()
+    torch.cuda.synchronize()
+    R = Replayer(env, n_sub)
+    R.check_initial_obs()
+    for k in range(n_steps):
+        a = action(k)
+        env.step(a)
+        torch.cuda.synchronize()
+        R.check_step(a)
+    s = R.summary()
+    v = torch.tensor([s["replayed_envs"], s["compared_env_steps"], s["mismatches"]], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(v, op=dist.ReduceOp.SUM)
+    return {"replayed_envs": int(v[0].item()), "replayed_steps": n_steps, "compared_env_steps": int(v[1].item()),
+            "mismatches": int(v[2].item()), "first_mismatches": s["first_mismatches"], "ranks": world,
+            "against": "oracle/td_oracle.c (C restatement pinned on the reference's golden vectors)",
+            "what": "first %d envs of every rank, batch at full size, auto-reset on, all outputs + observation bit-exact"
+                    % s["replayed_envs"]}
+
+
+def median(xs):
+    ys = sorted(xs)
+    return ys[len(ys) // 2] if len(ys) % 2 else 0.5 * (ys[len(ys) // 2 - 1] + ys[len(ys) // 2])
+
+
+def load_peak():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(name):
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return tr.get(name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def roofline_of(name, kind, n_envs, bytes_per_env_step, kernel_ms):
+    peak, src = load_peak()
+    achieved = bytes_per_env_step * n_envs / (kernel_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": load_traffic(name), "peak_source": src, "kernel": "td_step_kernel<%s>" % kind,
+            "algorithmic_bytes_per_launch": bytes_per_env_step * n_envs}
+
+
+def side_workload(torch, dist, args, name, rank, world, local, dev):
+    """One of BASELINE.json's other configs (3: def-middle multi-action, 4: atk-small, 5: 2p-large), timed the same
+    way (device events, median of the repeats) plus a short oracle replay at the full batch size."""
+    from gym_td_b200.vec_env import TDVecEnv
+    env_id, kind, L, n_envs, multi, bpe = WORKLOADS[name]
+    env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
+                   env_offset=1_000_000 * rank, multi_action=multi)
+    env.reset()
+    action, _, _ = make_actions(torch, name, kind, L, n_envs, multi, dev, 1234 + rank)
+    for k in range(args.preroll + args.warmup):
+        env.step(action(k))
+    steps = min(args.steps, 100)
+    ms = timed_repeats(torch, dist, env, action, steps, 3, world, dev)
+    m = median(ms) / steps
+    out = {"env_id": env_id, "envs_per_gpu": n_envs, "value": n_envs * max(world, 1) / (m * 1e-3), "unit": UNIT,
+           "ms_per_step": m, "steps": steps, "timed_repeats": len(ms),
+           "repeat_ms_per_step": [x / steps for x in ms],
+           "roofline": roofline_of(name, kind, n_envs, bpe, m)}
+    if args.replay > 0:
+        out["replay"] = replay_check(torch, dist, env, action, min(args.replay, 32), min(args.replay_steps, 60),
+                                     world, dev)
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     args = parse()
     quiet_stdout()
@@ -219,6 +370,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    cores_per_rank = pin_rank_to_cores(local, int(os.environ.get("LOCAL_WORLD_SIZE", str(world))))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -229,27 +381,7 @@ def main():
     env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
                    env_offset=1_000_000 * rank, multi_action=multi)
     env.reset()
-
-    # pre-generated synthetic actions, resident in HBM (excluded from the timed region)
-    g = torch.Generator(device=dev)
-    g.manual_seed(1234 + rank)
-    A = 16
-    def_pool = atk_pool = None
-    if kind != "atk":
-        if multi:
-            if args.workload.endswith("sparse"):     # SURVEY 8(d) config 3, second variant: each flag 1 with p = 0.01
-                def_pool = (torch.rand((4, n_envs, 6, L, L), device=dev, generator=g) < 0.01).to(torch.int64)
-            else:                                    # action_space.sample(): uniform {0, 1, 2}
-                def_pool = torch.randint(0, 3, (4, n_envs, 6, L, L), dtype=torch.int64, device=dev, generator=g)
-        else:
-            def_pool = torch.randint(0, 6 * L * L + 1, (A, n_envs), dtype=torch.int64, device=dev, generator=g)
-    if kind != "def":
-        atk_pool = torch.randint(0, 5, (A, n_envs, 3, 8), dtype=torch.int64, device=dev, generator=g)
-
-    def action(k):
-        d = def_pool[k % def_pool.shape[0]] if def_pool is not None else None
-        a = atk_pool[k % atk_pool.shape[0]] if atk_pool is not None else None
-        return d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+    action, def_pool, atk_pool = make_actions(torch, args.workload, kind, L, n_envs, multi, dev, 1234 + rank)
 
     def barrier():
         if world > 1:
@@ -264,23 +396,18 @@ def main():
     barrier()
 
     clocks = Clocks(local)
-    if rank == 0:
-        clocks.start()
-        time.sleep(0.25)
-    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    start.record()
-    for k in range(args.steps):
-        env.step(action(k))
-    end.record()
-    barrier()
-    ms = start.elapsed_time(end)
+
+    def start_clocks():
+        if rank == 0:
+            clocks.start()
+            time.sleep(0.25)
+            torch.cuda.synchronize()
+
+    # W warm-up steps are done; now `repeats` segments of exactly K steps each (median of 5)
+    seg_ms = timed_repeats(torch, dist, env, action, args.steps, args.repeats, world, dev, on_first=start_clocks)
     clk = clocks.stop() if rank == 0 else None
+    ms = median(seg_ms)
     stats = env.allreduce_stats()          # NCCL: the only collective of the path
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     value = n_envs * n_gpus * args.steps / (ms * 1e-3)
 
     # Opt-in variant (td_step_io.obs_incremental): the same float32 tensor, updated in place instead
@@ -306,6 +433,7 @@ def main():
 
     # end to end through the host-buffer API: pinned host actions in, reward/done/info out, every step
     e2e = None
+    e2e_obs = None
     if not args.no_e2e:
         hd = ha = None
         if kind != "atk":
@@ -321,22 +449,25 @@ def main():
         ke = max(10, args.steps // 3)
         for k in range(3):
             env.step_host(haction(k))
-        barrier()
-        t0 = time.perf_counter()
-        for k in range(ke):
-            out = env.step_host(haction(k))
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        tw = torch.tensor([wall], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        walls = []
+        for r in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(ke):
+                out = env.step_host(haction(k))
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            tw = torch.tensor([wall], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+            walls.append(float(tw.item()))
         h2d, d2h = env.host_bytes_per_step(False)
-        e2e = {"value": n_envs * n_gpus * ke / float(tw.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": ke,
+        e2e = {"value": n_envs * n_gpus * ke / median(walls), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": ke, "timed_repeats": len(walls),
                "note": "td_step_host: pinned host actions -> device, fused step, reward/done/win/allow/"
-                       "RealAction/FailCode -> host, stream sync every step; the observation stays in HBM "
-                       "for the on-device learner (see e2e_host_obs for the variant that also copies it)"}
-        e2e_obs = None
+                       "RealAction/FailCode -> host, stream sync every step (host wall clock, max over ranks, median "
+                       "of the repeats); the observation stays in HBM for the on-device learner (see e2e_host_obs "
+                       "for the variant that also copies it)"}
         if rank == 0 and world == 1:
             ko = 5
             env.step_host(haction(0), want_obs=True)
@@ -349,44 +480,51 @@ def main():
                        "d2h_bytes_per_step": d2h, "steps": ko,
                        "note": "as e2e plus the full float32 observation copied to pinned host memory (PCIe-bound)"}
 
+    replay = None
+    if args.replay > 0:
+        replay = replay_check(torch, dist, env, action, args.replay, args.replay_steps, world, dev)
+    env.close()
+    del env, def_pool, atk_pool
+    torch.cuda.empty_cache()
+
+    # BASELINE.json configs 3-5 next to the headline (N = 1 by default: they would triple every SCALE run)
+    sides = {}
+    if args.workload == "def-small" and not args.no_side_workloads and (world == 1 or args.side_workloads_multi):
+        for name in ("atk-small", "def-middle-multi", "2p-large"):
+            sides[name] = side_workload(torch, dist, args, name, rank, world, local, dev)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    peaks, peak_src = {}, "fallback"
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
     kernel_ms = ms / args.steps                      # one fused kernel per step, timed on its own stream
-    achieved = bytes_per_env_step * n_envs / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tr.get(args.workload, {}).get("dram_bytes_per_launch")
-    except Exception:
-        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 state / f32 observation", "data": "synthetic",
-        "config": dict(config_of(args, n_envs), preroll_steps=args.preroll),
-        "gpu_launches": args.steps,
+        "config": config_of(args, n_envs),
+        "preroll_steps": args.preroll,
+        "timing": {"timed_repeats": len(seg_ms), "steps_per_repeat": args.steps, "statistic": "median",
+                   "repeat_ms_per_step": [x / args.steps for x in seg_ms],
+                   "spread": (max(seg_ms) - min(seg_ms)) / ms if ms > 0 else None},
+        "gpu_launches": args.steps * len(seg_ms),
         "clocks": clk,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src,
-                     "kernel": "td_step_kernel<%s>" % kind, "algorithmic_bytes_per_launch": bytes_per_env_step * n_envs},
+        "roofline": roofline_of(args.workload, kind, n_envs, bytes_per_env_step, kernel_ms),
         "episode_stats": stats,
     }
+    if cores_per_rank:
+        line["host_cores_per_rank"] = cores_per_rank
     if inc is not None:
         line["incremental_obs"] = inc
     if e2e is not None:
         line["e2e"] = e2e
         if e2e_obs is not None:
             line["e2e_host_obs"] = e2e_obs
+    if replay is not None:
+        line["replay"] = replay
+    if sides:
+        line["workloads"] = sides
     if n_gpus == 1 and not args.no_cpu_baseline:
         from oracle import cpu_baseline as CB
         cores = os.cpu_count() or 1

@@ -1,0 +1,156 @@
+// storebench_l2.cu -- can a compact env-record array stay resident in L2 under the observation write stream?
+// (experiment, not product code; results in DESIGN.md section 7)
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/sbl tools/storebench_l2.cu && /tmp/sbl
+// storebench_read.cu showed: a dependent record read that hits L2 is free (0.168 ms), the same read from DRAM
+// costs 0.015 ms for the first 256 B and 0.013 ms per further KB, the write-back 0.007 ms per 512 B.
+// Here every env reads S bytes of its own record, writes its 18,000 B observation, writes WB bytes back;
+// records are S bytes apart (65,536 x S = 50 / 67 MB against the 126 MB L2).
+//   policy 0: plain ld / st everywhere
+//   policy 1: record ld/st with an L2 evict_last policy, observation stores plain
+//   policy 2: record evict_last, observation stores evict_first
+//   policy 3: record plain, observation stores evict_first
+//   policy 4: record evict_last, observation stores no L2 hint but st.global.cs
+// each also under a persisting access-policy window over the record array (`win`).
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
+constexpr int kN4 = 1125;
+
+__device__ __forceinline__ unsigned long long policy_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long policy_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ int4 ld_hint(const int4 *a, unsigned long long pol)
+{
+    int4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_hint(int4 *a, int4 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.s32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(float4 *a, float4 v, unsigned long long pol)
+{
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
+template <int S, int WB, int POLICY>
+__global__ void __launch_bounds__(128) k(float4 *out, int4 *rec, int n)
+{
+    extern __shared__ unsigned char smem[];
+    int env = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (env >= n) return;
+    if (rec == nullptr) smem[threadIdx.x] = 1;
+    const unsigned long long pl = policy_last(), pf = policy_first();
+    int4 *r = rec + (size_t)env * (S / 16);
+    int acc = 0;
+#pragma unroll
+    for (int k = 0; k < (S + 511) / 512; ++k)
+        if (lane + 32 * k < S / 16) {
+            int4 a = (POLICY == 1 || POLICY == 2 || POLICY == 4) ? ld_hint(r + lane + 32 * k, pl) : r[lane + 32 * k];
+            acc ^= a.x ^ a.y;
+        }
+    acc = __reduce_xor_sync(0xffffffffu, acc);
+    float v = (float)(acc & 1);
+    float4 *p = out + (size_t)env * kN4 + lane;
+    float4 x = make_float4(v, v, v, v);
+#pragma unroll 8
+    for (int k = 0; k < kN4 / 32; ++k) {
+        if (POLICY == 2 || POLICY == 3) st_hint(p + 32 * k, x, pf);
+        else if (POLICY == 4) __stcs(p + 32 * k, x);
+        else p[32 * k] = x;
+    }
+    if (lane < kN4 % 32) {
+        if (POLICY == 2 || POLICY == 3) st_hint(p + 32 * (kN4 / 32), x, pf);
+        else if (POLICY == 4) __stcs(p + 32 * (kN4 / 32), x);
+        else p[32 * (kN4 / 32)] = x;
+    }
+    if (lane < WB / 16) {
+        int4 w = make_int4(acc + 1, acc, 1, 1);
+        if (POLICY == 1 || POLICY == 2 || POLICY == 4) st_hint(r + lane, w, pl); else r[lane] = w;
+    }
+}
+
+template <typename F> float timeit(F f, cudaStream_t s, int iters = 30)
+{
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int i = 0; i < 5; ++i) f();
+    CK(cudaGetLastError());
+    cudaEventRecord(a, s);
+    for (int i = 0; i < iters; ++i) f();
+    cudaEventRecord(b, s);
+    CK(cudaEventSynchronize(b));
+    float ms; cudaEventElapsedTime(&ms, a, b);
+    return ms / iters;
+}
+
+template <int S, int WB>
+void sweep(cudaStream_t s, float4 *out, int4 *rec, int n, const char *tag)
+{
+    const size_t smem_bytes = (size_t)(227 * 1024 / 6 - 1024) & ~(size_t)127;      // 6 CTAs = 24 warps per SM
+    const int grid = n / 4;
+    auto run = [&](auto kern) {
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        return timeit([&] { kern<<<grid, 128, smem_bytes, s>>>(out, rec, n); }, s);
+    };
+    float t0 = run(k<S, WB, 0>), t1 = run(k<S, WB, 1>), t2 = run(k<S, WB, 2>), t3 = run(k<S, WB, 3>), t4 = run(k<S, WB, 4>);
+    printf("%-10s S=%4d WB=%3d (%5.1f MB of records): plain %.4f | rec last %.4f | rec last + obs first %.4f | obs first %.4f | rec last + obs .cs %.4f ms\n",
+           tag, S, WB, (double)n * S / 1e6, t0, t1, t2, t3, t4);
+}
+
+int main()
+{
+    const int n = 65536;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("L2 %.1f MB, persisting max %.1f MB, window max %.1f MB\n", prop.l2CacheSize / 1e6, prop.persistingL2CacheMaxSize / 1e6,
+           prop.accessPolicyMaxWindowSize / 1e6);
+    cudaStream_t s;
+    CK(cudaStreamCreate(&s));
+    float4 *out; int4 *rec;
+    CK(cudaMalloc(&out, (size_t)n * kN4 * 16)); CK(cudaMalloc(&rec, (size_t)n * 2048)); CK(cudaMemset(rec, 1, (size_t)n * 2048));
+    sweep<512, 256>(s, out, rec, n, "no window");
+    sweep<768, 384>(s, out, rec, n, "no window");
+    sweep<1024, 384>(s, out, rec, n, "no window");
+    sweep<1536, 512>(s, out, rec, n, "no window");
+    for (double frac : {0.25, 0.5, 0.75}) {
+        size_t aside = (size_t)(prop.persistingL2CacheMaxSize * frac);
+        CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, aside));
+        for (int S : {512, 768, 1024}) {
+            cudaStreamAttrValue av;
+            size_t bytes = (size_t)n * S;
+            av.accessPolicyWindow.base_ptr = rec;
+            av.accessPolicyWindow.num_bytes = bytes < (size_t)prop.accessPolicyMaxWindowSize ? bytes : prop.accessPolicyMaxWindowSize;
+            av.accessPolicyWindow.hitRatio = bytes <= aside ? 1.0f : (float)((double)aside / bytes);
+            av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+            CK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+            char tag[64];
+            snprintf(tag, sizeof tag, "win %.0fMB", aside / 1e6);
+            if (S == 512) sweep<512, 256>(s, out, rec, n, tag);
+            if (S == 768) sweep<768, 384>(s, out, rec, n, tag);
+            if (S == 1024) sweep<1024, 384>(s, out, rec, n, tag);
+        }
+        cudaStreamAttrValue off;
+        off.accessPolicyWindow.num_bytes = 0;
+        off.accessPolicyWindow.base_ptr = nullptr;
+        off.accessPolicyWindow.hitRatio = 0.f;
+        off.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        off.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        CK(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &off));
+        CK(cudaCtxResetPersistingL2Cache());
+    }
+    return 0;
+}
