@@ -328,10 +328,11 @@ def roofline_of(name, kind, n_envs, bytes_per_env_step, kernel_ms):
 def side_workload(torch, dist, args, name, rank, world, local, dev):
     """One of BASELINE.json's other configs (3: def-middle multi-action, 4: atk-small, 5: 2p-large), timed the same
     way (device events, median of the repeats) plus a short oracle replay at the full batch size."""
+    from gym_td_b200 import dist as D
     from gym_td_b200.vec_env import TDVecEnv
     env_id, kind, L, n_envs, multi, bpe = WORKLOADS[name]
     env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
-                   env_offset=1_000_000 * rank, multi_action=multi)
+                   env_offset=D.rank_env_offset(rank), multi_action=multi)
     env.reset()
     action, _, _ = make_actions(torch, name, kind, L, n_envs, multi, dev, 1234 + rank)
     for k in range(args.preroll + args.warmup):
@@ -361,6 +362,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    from gym_td_b200 import dist as D
     from gym_td_b200.vec_env import TDVecEnv
 
     rank = int(os.environ.get("RANK", "0"))
@@ -379,7 +381,7 @@ def main():
     env_id, kind, L, n_envs, multi, bytes_per_env_step = WORKLOADS[args.workload]
     n_envs = args.envs or n_envs
     env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
-                   env_offset=1_000_000 * rank, multi_action=multi)
+                   env_offset=D.rank_env_offset(rank), multi_action=multi)
     env.reset()
     action, def_pool, atk_pool = make_actions(torch, args.workload, kind, L, n_envs, multi, dev, 1234 + rank)
 

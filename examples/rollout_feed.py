@@ -6,7 +6,9 @@
 
 The observation tensor written by the step kernel is read directly by a small CNN (library convolutions:
 the learner is not part of this repo's hot path); actions are sampled on the GPU and handed back to the next
-step; nothing crosses PCIe.  For TD-def / TD-atk the RolloutBuffer records penalised rewards and computes GAE.
+step; nothing crosses PCIe.  A RolloutBuffer per player (one for TD-def / TD-atk, two for TD-2p) masks the actions
+by AllowNextMove, records the penalised rewards and computes GAE at the end of every horizon -- the host loop of
+the reference's trainer (train/main.py:79-176, train/PPO/Model.py:134-192) as device kernels.
 """
 import argparse
 import os
@@ -19,6 +21,7 @@ import torch
 import torch.distributed as dist
 
 import gym_td_b200 as G
+from gym_td_b200 import dist as D
 from gym_td_b200.rollout import RolloutBuffer
 
 
@@ -57,11 +60,13 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     # the policy reads env.obs in place and nothing else writes it: let the step update it incrementally
-    env = G.make_vec(args.env, args.envs, seed=0, device=local, env_offset=rank * 1_000_000, incremental_obs=True)
+    env = G.make_vec(args.env, args.envs, seed=0, device=local, env_offset=D.rank_env_offset(rank), incremental_obs=True)
     L, kind = env.map_size, env.kind
     policy = TinyPolicy(L).cuda(local).to(memory_format=torch.channels_last).eval()
-    buf = RolloutBuffer(env, horizon=args.horizon) if kind in ("def", "atk") else None
+    roles = {"def": ["defender"], "atk": ["attacker"], "2p": ["defender", "attacker"]}[kind]
+    bufs = [RolloutBuffer(env, horizon=args.horizon, role=r, keep_actions=False) for r in roles]
     values = torch.zeros((args.horizon, args.envs), dtype=torch.float32, device=env.device)
+    flushes = 0
     obs = env.reset()
     obs_ptr = obs.data_ptr()
     torch.cuda.synchronize()
@@ -72,20 +77,30 @@ def main():
             d_act = torch.distributions.Categorical(logits=d_logits.float()).sample()
             a_act = torch.distributions.Categorical(logits=a_logits.float()).sample()
             action = d_act if kind == "def" else a_act if kind == "atk" else {"Attacker": a_act, "Defender": d_act}
-            if buf is not None:
-                values[buf.ptr] = v.float()
-                buf.mask(action)
+            values[bufs[0].ptr] = v.float()
+            for b in bufs:
+                b.mask(action)
             obs, reward, done, info = env.step(action)
             assert obs.data_ptr() == obs_ptr
-            if buf is not None and buf.record(action):
-                buf.flush(values, policy(obs)[2].float())
+            full = [b.record(action) for b in bufs]
+            if full[0]:
+                nv = policy(obs)[2].float()
+                for b in bufs:                                  # zero-sum game: the attacker's critic is -V
+                    b.flush(values if b.role == "defender" or kind != "2p" else -values,
+                            nv if b.role == "defender" or kind != "2p" else -nv)
+                flushes += 1
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
     stats = env.allreduce_stats()
     if rank == 0:
+        import json
         print("%s: %d envs x %d ranks, %d steps with the policy in the loop: %.3g env-steps/s; episodes %d, wins %d"
               % (args.env, args.envs, world, args.steps, args.envs * world * args.steps / wall, stats["episodes"],
                  stats["wins"]))
+        print(json.dumps({"env_id": args.env, "envs_per_gpu": args.envs, "ranks": world, "steps": args.steps,
+                          "env_steps_per_sec_with_policy": args.envs * world * args.steps / wall,
+                          "players_recorded": roles, "horizon": args.horizon, "gae_flushes": flushes,
+                          "episode_stats": stats, "nccl": world > 1}))
     if world > 1:
         dist.destroy_process_group()
 

@@ -28,8 +28,16 @@ struct td_handle {
     td_stats *stats_dev;
     bool opponent_seeded;
     long long steps;
-    cudaStream_t pipe[2];          // internal streams of the chunked host path (td_step_host)
-    cudaEvent_t pipe_done[2], pipe_start;
+    // td_step_host: the whole host-buffer step (action copies, chunk kernels, output copies) is one CUDA graph,
+    // cached per distinct set of buffers
+    struct HostGraph { std::vector<unsigned char> key; cudaGraphExec_t exec; unsigned long long used; };
+    std::vector<HostGraph> host_graphs;
+    unsigned long long host_graph_clock;
+    cudaStream_t host_stream;      // stands in for the legacy default stream, which cannot launch graphs
+    int host_chunks;               // 0 = automatic
+    int host_graph;                // 1 = graph launch (default), 0 = plain stream launches
+    int step_smem_kb, obs_smem_kb; // experiments (td_set_option): lower the residency of the step / observe kernels
+    unsigned long long cfg_generation;
     td_config cfg;
     DevConfig dev_cfg;             // derived tables of cfg; copied into the parameters of every launch (per handle)
     std::string err;
@@ -53,6 +61,8 @@ static int fail(td_handle *h, int code, const std::string &msg)
 static int round16(int x) { return (x + 15) & ~15; }
 
 extern "C" int td_abi_version(void) { return TD_ABI_VERSION; }
+
+extern "C" int td_packed_stride(int env_kind) { return env_kind == TD_KIND_DEF ? 32 : (int)sizeof(td_step_packed); }
 
 extern "C" const char *td_last_error(const td_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
@@ -176,6 +186,7 @@ static int derive_config(td_handle *h, const td_config *c)
     d.def_interval = c->defender_action_interval;
     d.max_steps = c->max_episode_steps;
     h->cfg = *c;
+    h->cfg_generation += 1;      // cached host-step graphs carry the old tables in their kernel parameters
     return TD_OK;
 }
 
@@ -299,7 +310,8 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->obs_synced = nullptr;
     h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
     h->opponent_seeded = false; h->steps = 0;
-    h->pipe[0] = h->pipe[1] = nullptr; h->pipe_done[0] = h->pipe_done[1] = nullptr; h->pipe_start = nullptr;
+    h->host_graph_clock = 0; h->host_stream = nullptr; h->host_chunks = 0; h->host_graph = 1;
+    h->step_smem_kb = 0; h->obs_smem_kb = 0; h->cfg_generation = 0;
     td_config def;
     if (!cfg) { td_default_config(&def); cfg = &def; }
     int rc = validate_config(h, cfg);
@@ -342,11 +354,8 @@ extern "C" int td_destroy(td_handle *h)
     if (h->mt) cudaFree(h->mt);
     if (h->stats) cudaFree(h->stats);
     if (h->stats_dev) cudaFree(h->stats_dev);
-    for (int k = 0; k < 2; ++k) {
-        if (h->pipe[k]) cudaStreamDestroy(h->pipe[k]);
-        if (h->pipe_done[k]) cudaEventDestroy(h->pipe_done[k]);
-    }
-    if (h->pipe_start) cudaEventDestroy(h->pipe_start);
+    for (auto &g : h->host_graphs) cudaGraphExecDestroy(g.exec);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
     delete h;
     return TD_OK;
 }
@@ -554,6 +563,10 @@ static int check_io(td_handle *h, const td_step_io *io)
     if (h->kind != TD_KIND_ATK && !io->def_action_dev) return fail(h, TD_E_INVALID, "td_step: def_action_dev is required");
     if (h->kind != TD_KIND_DEF && !io->atk_action_dev) return fail(h, TD_E_INVALID, "td_step: atk_action_dev is required");
     if (h->kind == TD_KIND_ATK && io->multi_action) return fail(h, TD_E_INVALID, "td_step: multi_action does not apply to the attacker env");
+    if (h->kind != TD_KIND_DEF && (io->opponent_dev || io->opponent_cluster_dev))
+        return fail(h, TD_E_INVALID, "td_step: opponent_dev / opponent_cluster_dev belong to the defender env");
+    if (io->opponent_dev && io->opponent_cluster_dev)
+        return fail(h, TD_E_INVALID, "td_step: give opponent_dev or opponent_cluster_dev, not both");
     return TD_OK;
 }
 
@@ -564,7 +577,16 @@ static bool obs_is_current(const td_handle *h, const td_step_io *io)
     return io->obs_incremental != 0 && io->obs_dev != nullptr && io->obs_dev == h->obs_synced;
 }
 
-static int launch_step(td_handle *h, const td_step_io *io, int begin, int count, cudaStream_t s, bool incremental)
+// Where a step kernel goes: straight onto a stream, or into a graph under construction (td_step_host).
+struct LaunchTarget {
+    cudaStream_t stream = nullptr;
+    cudaGraph_t graph = nullptr;
+    const cudaGraphNode_t *deps = nullptr;
+    size_t n_deps = 0;
+    cudaGraphNode_t node = nullptr;      // out: the kernel node that was added
+};
+
+static int launch_step(td_handle *h, const td_step_io *io, int begin, int count, LaunchTarget &t, bool incremental)
 {
     StepParams p;
     fill_params(h, p);
@@ -574,19 +596,29 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
     const int per_cta = kWarpsPerCta * 32 / step_group_width(h);         // game instances per CTA
     const int grid = (count + per_cta - 1) / per_cta, block = kWarpsPerCta * 32;
     size_t smem = step_smem_bytes(h);
-    static const int pad_kb = getenv("TD_STEP_SMEM_KB") ? atoi(getenv("TD_STEP_SMEM_KB")) : 0;   // experiments
-    if (pad_kb > 0 && (size_t)pad_kb * 1024 > smem) {
-        smem = (size_t)pad_kb * 1024;
+    if (h->step_smem_kb > 0 && (size_t)h->step_smem_kb * 1024 > smem) {       // experiments (td_set_option)
+        smem = (size_t)h->step_smem_kb * 1024;
         for_each_step_kernel(h, incremental, [&](auto kernel) { return allow_smem(kernel, smem); });
     }
     const int want = step_variant(h->kind, io->multi_action != 0);
     int seen = 0;
     cudaError_t le = for_each_step_kernel(h, incremental, [&](auto kernel) {
-        if (seen++ == want) kernel<<<grid, block, smem, s>>>(p);
-        return cudaSuccess;
+        if (seen++ != want) return cudaSuccess;
+        if (!t.graph) {
+            kernel<<<grid, block, smem, t.stream>>>(p);
+            return cudaGetLastError();
+        }
+        void *args[] = {&p};
+        cudaKernelNodeParams kp;
+        memset(&kp, 0, sizeof(kp));
+        kp.func = reinterpret_cast<void *>(kernel);
+        kp.gridDim = dim3(grid);
+        kp.blockDim = dim3(block);
+        kp.sharedMemBytes = (unsigned)smem;
+        kp.kernelParams = args;
+        return cudaGraphAddKernelNode(&t.node, t.graph, t.deps, t.n_deps, &kp);
     });
     if (le != cudaSuccess) return fail(h, TD_E_CUDA, std::string("td_step: ") + cudaGetErrorString(le));
-    TD_CUDA(h, cudaGetLastError());
     return TD_OK;
 }
 
@@ -596,7 +628,9 @@ extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
     int rc = check_io(h, io);
     if (rc != TD_OK) return rc;
     TD_CUDA(h, cudaSetDevice(h->device));
-    rc = launch_step(h, io, 0, h->n_envs, (cudaStream_t)stream, obs_is_current(h, io));
+    LaunchTarget t;
+    t.stream = (cudaStream_t)stream;
+    rc = launch_step(h, io, 0, h->n_envs, t, obs_is_current(h, io));
     if (rc != TD_OK) return rc;
     h->obs_synced = io->obs_dev;
     h->steps += h->n_envs;
@@ -613,8 +647,8 @@ extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
     fill_params(h, p);
     const int grid = grid_of(h), block = kWarpsPerCta * 32;
     size_t smem = smem_of(h);
-    if (const char *ev = getenv("TD_OBS_SMEM_KB")) {            // experiments: throttle occupancy of the store kernel
-        smem = std::max(smem, (size_t)atoi(ev) * 1024);
+    if (h->obs_smem_kb > 0) {                                   // experiments (td_set_option)
+        smem = std::max(smem, (size_t)h->obs_smem_kb * 1024);
         cudaFuncSetAttribute(td_observe_kernel<100>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     cudaStream_t s = (cudaStream_t)stream;
@@ -665,6 +699,123 @@ extern "C" int td_observe_snapshot(td_handle *h, const void *records_dev, int n,
     return TD_OK;
 }
 
+// One host-buffer step as a list of operations: per chunk of envs the action copies (host -> device), the step
+// kernel, the output copies (device -> host).  The kernels run in chunk order; a chunk's input copy overlaps the
+// kernels before it and its output copy the kernels after it (instances are independent, so a chunk is a
+// complete unit of work).  The list is either instantiated once as a CUDA graph and replayed with one launch
+// (default), or issued on the stream call by call (TD_OPT_HOST_GRAPH = 0, pageable host memory).
+struct HostCopy { void *dst; const void *src; size_t bytes; };
+
+static void host_chunk_copies(const td_handle *h, const td_step_io *io, const td_host_io *host, size_t b, size_t n,
+                              std::vector<HostCopy> &in, std::vector<HostCopy> &out)
+{
+    const size_t cells = (size_t)h->cells;
+    const size_t def_w = io->multi_action ? 6 * cells : 1;               // int64 elements per env
+    const size_t atk_w = TD_ROADS * TD_CLUSTER;
+    in.clear();
+    out.clear();
+    if (h->kind != TD_KIND_ATK)
+        in.push_back({(int64_t *)io->def_action_dev + b * def_w, host->def_action_host + b * def_w, n * def_w * 8});
+    if (h->kind != TD_KIND_DEF)
+        in.push_back({(int64_t *)io->atk_action_dev + b * atk_w, host->atk_action_host + b * atk_w, n * atk_w * 8});
+    if (h->kind == TD_KIND_ATK && io->def_action_dev && host->def_action_host)       // host-resolved scripted defender
+        in.push_back({(int64_t *)io->def_action_dev + b, host->def_action_host + b, n * 8});
+    if (io->opponent_dev && host->opponent_host)
+        in.push_back({(uint8_t *)io->opponent_dev + b, host->opponent_host + b, n});
+    if (io->opponent_cluster_dev && host->opponent_cluster_host)
+        in.push_back({(uint32_t *)io->opponent_cluster_dev + b, host->opponent_cluster_host + b, n * 4});
+    // device -> host: outputs that sit at matching offsets of one device slab and one host slab (as TDVecEnv
+    // allocates them) are merged into a single copy when the chunk is the whole batch
+    struct Seg { char *dst; const char *src; size_t bytes; };
+    Seg segs[9];
+    int ns = 0;
+    auto add = [&](void *dst, const void *src, size_t elem_bytes) {
+        if (dst && src)
+            segs[ns++] = Seg{static_cast<char *>(dst) + b * elem_bytes, static_cast<const char *>(src) + b * elem_bytes,
+                             n * elem_bytes};
+    };
+    add(host->obs_host, io->obs_dev, TD_NCHANNELS * cells * sizeof(float));
+    add(host->reward_host, io->reward_dev, sizeof(double));
+    add(host->done_host, io->done_dev, 1);
+    add(host->win_host, io->win_dev, 1);
+    add(host->allow_next_host, io->allow_next_dev, 1);
+    if (h->kind != TD_KIND_ATK) add(host->real_def_host, io->real_def_dev, def_w * 8);
+    if (h->kind != TD_KIND_DEF) add(host->real_atk_host, io->real_atk_dev, atk_w * 8);
+    if (h->kind != TD_KIND_ATK) add(host->fail_def_host, io->fail_def_dev, sizeof(int32_t));
+    if (h->kind != TD_KIND_DEF) add(host->fail_atk_host, io->fail_atk_dev, 4 * sizeof(int32_t));
+    std::sort(segs, segs + ns, [](const Seg &x, const Seg &y) { return x.src < y.src; });
+    for (int i = 0; i < ns;) {
+        Seg m = segs[i];
+        int j = i + 1;
+        while (j < ns && segs[j].src >= m.src + m.bytes && segs[j].src - (m.src + m.bytes) <= 256 &&
+               segs[j].src - m.src == segs[j].dst - m.dst) {
+            m.bytes = (size_t)(segs[j].src - m.src) + segs[j].bytes;
+            ++j;
+        }
+        out.push_back({m.dst, m.src, m.bytes});
+        i = j;
+    }
+}
+
+static bool host_pointer_is_pinned(const void *p)
+{
+    if (!p) return true;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static int host_chunk_count(const td_handle *h, const td_host_io *host)
+{
+    // measured on B200 (def-small, 65,536 envs, tools/e2e_sweep.py): every extra chained chunk costs ~10 us of kernel
+    // boundary, more than the copy time it hides (1 / 2 / 4 chunks: 0.290 / 0.301 / 0.326 ms per step), so one chunk
+    // is the default; only the PCIe-bound variant that also ships the observation gains from cutting
+    int chunks = h->host_chunks;
+    if (chunks <= 0) chunks = host->obs_host ? 8 : 1;
+    return std::max(1, std::min(chunks, h->n_envs));
+}
+
+static int build_host_graph(td_handle *h, const td_step_io *io, const td_host_io *host, int chunks, bool incremental,
+                            cudaGraphExec_t *exec_out)
+{
+    cudaGraph_t g = nullptr;
+    TD_CUDA(h, cudaGraphCreate(&g, 0));
+    auto bail = [&](int rc) { cudaGraphDestroy(g); return rc; };
+    const int base = h->n_envs / chunks, rem = h->n_envs % chunks;
+    std::vector<HostCopy> in, out;
+    cudaGraphNode_t prev_kernel = nullptr;
+    int begin = 0;
+    for (int c = 0; c < chunks; ++c) {
+        const int count = base + (c < rem ? 1 : 0);
+        host_chunk_copies(h, io, host, (size_t)begin, (size_t)count, in, out);
+        std::vector<cudaGraphNode_t> deps;
+        for (const HostCopy &cp : in) {
+            cudaGraphNode_t n;
+            cudaError_t e = cudaGraphAddMemcpyNode1D(&n, g, nullptr, 0, cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) return bail(fail(h, TD_E_CUDA, std::string("td_step_host: memcpy node: ") + cudaGetErrorString(e)));
+            deps.push_back(n);
+        }
+        if (prev_kernel) deps.push_back(prev_kernel);
+        LaunchTarget t;
+        t.graph = g;
+        t.deps = deps.data();
+        t.n_deps = deps.size();
+        int rc = launch_step(h, io, begin, count, t, incremental);
+        if (rc != TD_OK) return bail(rc);
+        for (const HostCopy &cp : out) {
+            cudaGraphNode_t n;
+            cudaError_t e = cudaGraphAddMemcpyNode1D(&n, g, &t.node, 1, cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) return bail(fail(h, TD_E_CUDA, std::string("td_step_host: memcpy node: ") + cudaGetErrorString(e)));
+        }
+        prev_kernel = t.node;
+        begin += count;
+    }
+    cudaError_t e = cudaGraphInstantiate(exec_out, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return fail(h, TD_E_CUDA, std::string("td_step_host: cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    return TD_OK;
+}
+
 extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, void *stream)
 {
     if (!h) return TD_E_INVALID;
@@ -675,86 +826,120 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
     if (h->kind != TD_KIND_DEF && !host->atk_action_host) return fail(h, TD_E_INVALID, "td_step_host: atk_action_host is required");
     TD_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t cells = (size_t)h->cells;
-    const size_t def_w = io->multi_action ? 6 * cells : 1;               // int64 elements per env
-    const size_t atk_w = TD_ROADS * TD_CLUSTER;
-    static const int forced = getenv("TD_HOST_CHUNKS") ? atoi(getenv("TD_HOST_CHUNKS")) : 0;
-    // measured on B200 (def-small, 65,536 envs): 1 chunk 2.06e8, 2 chunks 2.06e8, 4 chunks 1.84e8 env-steps/s --
-    // the host path is bound by launch/sync latency, not by the copies, so one chunk is the default.
-    int chunks = forced > 0 ? forced : 1;
-    if (chunks > h->n_envs) chunks = 1;
-    if (chunks > 1 && !h->pipe[0]) {
-        for (int k = 0; k < 2; ++k) {
-            TD_CUDA(h, cudaStreamCreateWithFlags(&h->pipe[k], cudaStreamNonBlocking));
-            TD_CUDA(h, cudaEventCreateWithFlags(&h->pipe_done[k], cudaEventDisableTiming));
+    td_step_io io_packed;
+    if (host->packed_host) {
+        // zero-copy outputs: the kernel stores every env's packed record straight into the caller's page-locked buffer
+        void *dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, host->packed_host, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(h, TD_E_INVALID, "td_step_host: packed_host must be page-locked, device-mapped host memory");
         }
-        TD_CUDA(h, cudaEventCreateWithFlags(&h->pipe_start, cudaEventDisableTiming));
+        io_packed = *io;
+        io_packed.packed_out_dev = dptr;
+        io = &io_packed;
     }
-    if (chunks > 1) {
-        TD_CUDA(h, cudaEventRecord(h->pipe_start, s));
-        for (int k = 0; k < 2; ++k) TD_CUDA(h, cudaStreamWaitEvent(h->pipe[k], h->pipe_start, 0));
-    }
-    const int base = h->n_envs / chunks, rem = h->n_envs % chunks;
     const bool incremental = obs_is_current(h, io);
+    const int chunks = host_chunk_count(h, host);
     h->obs_synced = nullptr;                                    // until every chunk was launched
-    int begin = 0;
-    for (int c = 0; c < chunks; ++c) {
-        const int count = base + (c < rem ? 1 : 0);
-        const size_t b = (size_t)begin, n = (size_t)count;
-        cudaStream_t st = chunks > 1 ? h->pipe[c & 1] : s;
-        if (h->kind != TD_KIND_ATK)
-            TD_CUDA(h, cudaMemcpyAsync((int64_t *)io->def_action_dev + b * def_w, host->def_action_host + b * def_w,
-                                       n * def_w * 8, cudaMemcpyHostToDevice, st));
-        if (h->kind != TD_KIND_DEF)
-            TD_CUDA(h, cudaMemcpyAsync((int64_t *)io->atk_action_dev + b * atk_w, host->atk_action_host + b * atk_w,
-                                       n * atk_w * 8, cudaMemcpyHostToDevice, st));
-        if (io->opponent_dev && host->opponent_host)
-            TD_CUDA(h, cudaMemcpyAsync((uint8_t *)io->opponent_dev + b, host->opponent_host + b, n, cudaMemcpyHostToDevice, st));
-        rc = launch_step(h, io, begin, count, st, incremental);
-        if (rc != TD_OK) return rc;
-        // device -> host for this chunk: outputs that sit at matching offsets of one device slab and one host
-        // slab (as TDVecEnv allocates them) are merged into a single copy when the chunk is the whole batch
-        struct Seg { char *dst; const char *src; size_t bytes; };
-        Seg segs[9];
-        int ns = 0;
-        auto add = [&](void *dst, const void *src, size_t elem_bytes) {
-            if (dst && src)
-                segs[ns++] = Seg{static_cast<char *>(dst) + b * elem_bytes, static_cast<const char *>(src) + b * elem_bytes,
-                                 n * elem_bytes};
-        };
-        add(host->obs_host, io->obs_dev, TD_NCHANNELS * cells * sizeof(float));
-        add(host->reward_host, io->reward_dev, sizeof(double));
-        add(host->done_host, io->done_dev, 1);
-        add(host->win_host, io->win_dev, 1);
-        add(host->allow_next_host, io->allow_next_dev, 1);
-        if (h->kind != TD_KIND_ATK) add(host->real_def_host, io->real_def_dev, def_w * 8);
-        if (h->kind != TD_KIND_DEF) add(host->real_atk_host, io->real_atk_dev, atk_w * 8);
-        if (h->kind != TD_KIND_ATK) add(host->fail_def_host, io->fail_def_dev, sizeof(int32_t));
-        if (h->kind != TD_KIND_DEF) add(host->fail_atk_host, io->fail_atk_dev, 4 * sizeof(int32_t));
-        std::sort(segs, segs + ns, [](const Seg &x, const Seg &y) { return x.src < y.src; });
-        for (int i = 0; i < ns;) {
-            Seg m = segs[i];
-            int j = i + 1;
-            while (j < ns && segs[j].src >= m.src + m.bytes && segs[j].src - (m.src + m.bytes) <= 256 &&
-                   segs[j].src - m.src == segs[j].dst - m.dst) {
-                m.bytes = (size_t)(segs[j].src - m.src) + segs[j].bytes;
-                ++j;
-            }
-            TD_CUDA(h, cudaMemcpyAsync(m.dst, m.src, m.bytes, cudaMemcpyDeviceToHost, st));
-            i = j;
-        }
-        begin += count;
+
+    bool use_graph = h->host_graph != 0;
+    if (use_graph) {
+        // a graph keeps raw host addresses: only page-locked buffers qualify
+        const void *hp[] = {host->def_action_host, host->atk_action_host, host->opponent_host, host->obs_host,
+                            host->reward_host, host->done_host, host->win_host, host->allow_next_host,
+                            host->real_def_host, host->real_atk_host, host->fail_def_host, host->fail_atk_host,
+                            host->opponent_cluster_host, host->packed_host};
+        for (const void *p : hp) use_graph = use_graph && host_pointer_is_pinned(p);
     }
-    if (chunks > 1) {
-        for (int k = 0; k < 2; ++k) {
-            TD_CUDA(h, cudaEventRecord(h->pipe_done[k], h->pipe[k]));
-            TD_CUDA(h, cudaStreamWaitEvent(s, h->pipe_done[k], 0));
+    if (use_graph) {
+        if (s == nullptr || s == cudaStreamLegacy) {
+            // the legacy default stream cannot launch a graph: a blocking internal stream takes its place (work on
+            // it is ordered after everything already in the legacy stream, and the call synchronises it below)
+            if (!h->host_stream) TD_CUDA(h, cudaStreamCreateWithFlags(&h->host_stream, cudaStreamDefault));
+            s = h->host_stream;
+        }
+        std::vector<unsigned char> key(sizeof(td_step_io) + sizeof(td_host_io) + 3 * sizeof(unsigned long long));
+        unsigned long long extra[3] = {(unsigned long long)chunks, incremental ? 1ull : 0ull, h->cfg_generation};
+        memcpy(key.data(), io, sizeof(td_step_io));
+        memcpy(key.data() + sizeof(td_step_io), host, sizeof(td_host_io));
+        memcpy(key.data() + sizeof(td_step_io) + sizeof(td_host_io), extra, sizeof(extra));
+        std::vector<unsigned char> state(2 * sizeof(int) + sizeof(void *) * 3);
+        // everything else a kernel node bakes in: map pool, generators, difficulty
+        {
+            const void *ptrs[3] = {h->maps, h->mt, h->records};
+            int ints[2] = {h->difficulty | (h->opponent_seeded ? 0x100 : 0) | (h->map_stride << 9), h->n_maps};
+            memcpy(state.data(), ints, sizeof(ints));
+            memcpy(state.data() + sizeof(ints), ptrs, sizeof(ptrs));
+        }
+        key.insert(key.end(), state.begin(), state.end());
+        td_handle::HostGraph *hit = nullptr;
+        for (auto &g : h->host_graphs)
+            if (g.key == key) { hit = &g; break; }
+        if (!hit) {
+            cudaGraphExec_t exec = nullptr;
+            rc = build_host_graph(h, io, host, chunks, incremental, &exec);
+            if (rc != TD_OK) return rc;
+            if (h->host_graphs.size() >= 16) {                      // evict the least recently used
+                size_t lru = 0;
+                for (size_t i = 1; i < h->host_graphs.size(); ++i)
+                    if (h->host_graphs[i].used < h->host_graphs[lru].used) lru = i;
+                cudaGraphExecDestroy(h->host_graphs[lru].exec);
+                h->host_graphs.erase(h->host_graphs.begin() + (long)lru);
+            }
+            h->host_graphs.push_back({key, exec, 0});
+            hit = &h->host_graphs.back();
+        }
+        hit->used = ++h->host_graph_clock;
+        TD_CUDA(h, cudaGraphLaunch(hit->exec, s));
+    } else {
+        // plain stream launches, chunk by chunk (pageable host memory or TD_OPT_HOST_GRAPH = 0)
+        const int base = h->n_envs / chunks, rem = h->n_envs % chunks;
+        std::vector<HostCopy> in, out;
+        int begin = 0;
+        for (int c = 0; c < chunks; ++c) {
+            const int count = base + (c < rem ? 1 : 0);
+            host_chunk_copies(h, io, host, (size_t)begin, (size_t)count, in, out);
+            for (const HostCopy &cp : in) TD_CUDA(h, cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice, s));
+            LaunchTarget t;
+            t.stream = s;
+            rc = launch_step(h, io, begin, count, t, incremental);
+            if (rc != TD_OK) return rc;
+            for (const HostCopy &cp : out) TD_CUDA(h, cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyDeviceToHost, s));
+            begin += count;
         }
     }
     h->obs_synced = io->obs_dev;
     h->steps += h->n_envs;
     TD_CUDA(h, cudaStreamSynchronize(s));
     return TD_OK;
+}
+
+extern "C" int td_invalidate_obs(td_handle *h)
+{
+    if (!h) return TD_E_INVALID;
+    h->obs_synced = nullptr;
+    return TD_OK;
+}
+
+extern "C" int td_set_option(td_handle *h, int option, int value)
+{
+    if (!h) return TD_E_INVALID;
+    switch (option) {
+    case TD_OPT_HOST_CHUNKS:
+        if (value < 0) return fail(h, TD_E_INVALID, "td_set_option: host chunks < 0");
+        h->host_chunks = value;
+        return TD_OK;
+    case TD_OPT_HOST_GRAPH: h->host_graph = value != 0; return TD_OK;
+    case TD_OPT_STEP_SMEM_KB:
+        if (value < 0 || value > 227) return fail(h, TD_E_INVALID, "td_set_option: shared memory out of range");
+        h->step_smem_kb = value;
+        return TD_OK;
+    case TD_OPT_OBS_SMEM_KB:
+        if (value < 0 || value > 227) return fail(h, TD_E_INVALID, "td_set_option: shared memory out of range");
+        h->obs_smem_kb = value;
+        return TD_OK;
+    default: return fail(h, TD_E_INVALID, "td_set_option: unknown option");
+    }
 }
 
 extern "C" int td_get_state(td_handle *h, int first_env, int n, void *blob)
@@ -852,6 +1037,13 @@ extern "C" int td_gae(int horizon, int n, const float *rewards_dev, const uint8_
 {
     if (horizon < 1 || n < 1 || !rewards_dev || !dones_dev || !values_dev || !next_value_dev || !advs_dev || !returns_dev)
         return fail(nullptr, TD_E_INVALID, "td_gae: bad arguments");
+    // no handle here: launch on the device that owns the buffers, whatever device is current on this thread
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, rewards_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        return fail(nullptr, TD_E_INVALID, "td_gae: rewards_dev is not a device pointer");
+    }
+    if (cudaSetDevice(attr.device) != cudaSuccess) return fail(nullptr, TD_E_CUDA, "td_gae: cudaSetDevice failed");
     gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(horizon, n, rewards_dev, dones_dev, values_dev,
                                                                 next_value_dev, gamma, lam, advs_dev, returns_dev);
     cudaError_t e = cudaGetLastError();

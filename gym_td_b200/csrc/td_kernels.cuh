@@ -34,8 +34,23 @@
 #define TD_ST(p, v) __stcs((p), (v))
 #elif TD_STORE_MODE == 1
 #define TD_ST(p, v) (*(p) = (v))
-#else
+#elif TD_STORE_MODE == 2
 #define TD_ST(p, v) __stwt((p), (v))
+#else
+// L2 evict_first policy on the observation stream: the env records keep their place in L2 (tools/storebench_l2.cu)
+__device__ __forceinline__ void td_st_first(float4 *a, float4 v)
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void td_st_first(float *a, float v)
+{
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(a), "f"(v), "l"(pol) : "memory");
+}
+#define TD_ST(p, v) td_st_first((p), (v))
 #endif
 // Debug build (-DTD_DEBUG_BOUNDS): index invariants are checked on the device and a violation sets the sticky
 // flag bit 2 of the env, which TDVecEnv.stats() / the parity tests surface.  (compute-sanitizer is closed on
@@ -68,8 +83,14 @@ constexpr int kMtWords = 624;
 // behind the scratch area of a slice: the tower / enemy cells of the env before the step (incremental observation)
 constexpr int kOldListBytes = 16 + 4 * TD_CAP_TOWERS + 4 * TD_CAP_ENEMIES;
 constexpr int kTwistStageBytes = kMtWords * 4;   // staging area of the generator regeneration (tail of a slice)
-constexpr int kSpecTowers = 16;           // speculatively staged list prefixes
-constexpr int kSpecEnemies = 16;
+#ifndef TD_SPEC_TOWERS
+#define TD_SPEC_TOWERS 16
+#endif
+#ifndef TD_SPEC_ENEMIES
+#define TD_SPEC_ENEMIES 16
+#endif
+constexpr int kSpecTowers = TD_SPEC_TOWERS;     // speculatively staged list prefixes
+constexpr int kSpecEnemies = TD_SPEC_ENEMIES;
 
 // Derived constant tables (uploaded by td_set_config).
 struct DevConfig {
@@ -341,29 +362,54 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
 // One window of tempered words lives in the lanes (lane i holds the i-th next word) and is consumed with a
 // shuffle per draw.  It is refilled first from the words cached in the record (no memory round trip), then from
 // the generator state in HBM (twisting it when exhausted).  `ck` counts cached words moved into a window.
+// Out of line and by value: the draw sites (a dozen in the scripted defender) share one copy of the refill, and
+// the context stays in registers (a by-reference context would be forced to local memory).
+#ifndef TD_REFILL_NOINLINE
+#define TD_REFILL_NOINLINE 0      // measured on B200: out of line costs the attacker env 1.5 % (0.2715 -> 0.2754 ms)
+#endif
+#if TD_REFILL_NOINLINE
+#define TD_REFILL_ATTR __noinline__
+#else
+#define TD_REFILL_ATTR __forceinline__
+#endif
+struct MtRefill { uint32_t win; int ck, win_n, mt_pos; };
+__device__ TD_REFILL_ATTR MtRefill mt_refill(const uint32_t *cache, uint32_t *mt, uint32_t *stage, int lane, int G,
+                                           unsigned gmask, int ck, int cn, int mt_pos)
+{
+    MtRefill r;
+    uint32_t y = 0u;
+    if (ck < cn) {
+        const int n = min(G, cn - ck);
+        if (lane < n) y = cache[ck + lane];
+        ck += n;
+        r.win_n = n;
+    } else {
+        if (mt_pos >= kMtWords) { mt_twist_staged(mt, stage, lane, G, gmask); mt_pos = 0; }
+        const int n = min(G, kMtWords - mt_pos);
+        if (lane < n) y = mt[mt_pos + lane];
+        r.win_n = n;
+    }
+    r.win = mt_temper(y);
+    r.ck = ck;
+    r.mt_pos = mt_pos;
+    return r;
+}
+
 template <class W>
 __device__ __forceinline__ void mt_fill_window(W &w)
 {
-    uint32_t y = 0u;
-    if (w.ck < w.cn) {
-        const int n = min(W::G, w.cn - w.ck);
-        if (w.lane < n) y = w.rng_cache()[w.ck + w.lane];
-        w.ck += n;
-        w.win_n = n;
-    } else {
-        if (w.mt_pos >= kMtWords) { mt_twist_staged(w.mt, w.twist_stage(), w.lane, W::G, w.gmask); w.mt_pos = 0; }
-        const int n = min(W::G, kMtWords - w.mt_pos);
-        if (w.lane < n) y = w.mt[w.mt_pos + w.lane];
-        w.win_n = n;
-    }
-    w.win = mt_temper(y);
+    const MtRefill r = mt_refill(w.rng_cache(), w.mt, w.twist_stage(), w.lane, W::G, w.gmask, w.ck, w.cn, w.mt_pos);
+    w.win = r.win;
+    w.ck = r.ck;
+    w.win_n = r.win_n;
+    w.mt_pos = r.mt_pos;
     w.win_k = 0;
 }
 
 template <class W>
 __device__ __forceinline__ uint32_t mt_next(W &w)
 {
-    if (w.win_k == w.win_n) mt_fill_window(w);
+    if (__builtin_expect(w.win_k == w.win_n, 0)) mt_fill_window(w);
     const uint32_t r = gshfl(w, w.win, w.win_k);
     ++w.win_k;
     ++w.mt_pos;
@@ -386,7 +432,7 @@ __device__ __forceinline__ void finish_env_load(W &w, const StepParams &p, const
 {
     pull_header(w);
     w.mt = mt_base;
-    if (w.nt > kSpecTowers || w.ne > kSpecEnemies) {
+    if (__builtin_expect(w.nt > kSpecTowers || w.ne > kSpecEnemies, 0)) {
         if (w.nt > kSpecTowers)
             async_copy16(w.tw() + kSpecTowers, rec + w.off_towers() + kSpecTowers * kTowerBytes, w.nt - kSpecTowers, w.lane, W::G);
         if (w.ne > kSpecEnemies)
@@ -817,15 +863,22 @@ __device__ __forceinline__ void summon_uniform(W &w, int t, int road)
 // ------------------------------------------------------------------------------------------------
 // scripted opponents on the device generator (TDGymBasic.py:81-196, random_agent=True)
 
+// host_cluster != 0xffffffff: the eight types and the road were drawn by the host (td_step_io.opponent_cluster_dev)
 template <class W>
-__device__ __forceinline__ void opponent_enemy(W &w, int difficulty)
+__device__ __forceinline__ void opponent_enemy(W &w, int difficulty, unsigned host_cluster)
 {
     const DevConfig &cc = w.pp->cfg;
     if (w.atk_cd != 0) return;
     if (difficulty == 0) {                                   // random_enemy_lv0
         long long mine = 0;
-        for (int k = 0; k < TD_CLUSTER; ++k) { int t = py_randbelow(w, TD_NTYPES + 1); if (w.lane == k) mine = t; }
-        int road = py_randbelow(w, w.mh()->num_roads);
+        int road;
+        if (host_cluster != 0xffffffffu) {
+            mine = w.lane < TD_CLUSTER ? (long long)((host_cluster >> (2 * w.lane)) & 3u) : 0ll;
+            road = min((int)((host_cluster >> 16) & 3u), w.mh()->num_roads - 1);
+        } else {
+            for (int k = 0; k < TD_CLUSTER; ++k) { int t = py_randbelow(w, TD_NTYPES + 1); if (w.lane == k) mine = t; }
+            road = py_randbelow(w, w.mh()->num_roads);
+        }
         summon_cluster(w, road, mine, 0);
     } else {                                                 // random_enemy_lv1
         int t = py_randbelow(w, TD_NTYPES);
@@ -1455,6 +1508,9 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 #ifndef TD_MIN_BLOCKS
 #define TD_MIN_BLOCKS 6
 #endif
+#ifndef TD_MIN_BLOCKS_ATK
+#define TD_MIN_BLOCKS_ATK TD_MIN_BLOCKS
+#endif
 
 // One env's rules for one step: load the record, apply the actions / scripted opponent, advance the board, emit
 // the per-env outputs, auto-reset.  Leaves the updated record in the slice and starts the asynchronous copy of
@@ -1466,14 +1522,18 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
     constexpr int GW = W::G;
     const int lane = w.lane;
     const td_step_io &io = p.io;
-    const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr &&
-                                 !(KIND == TD_KIND_DEF && io.opponent_dev != nullptr);
+    const bool host_opponent = (KIND == TD_KIND_DEF && (io.opponent_dev != nullptr || io.opponent_cluster_dev != nullptr)) ||
+                               (KIND == TD_KIND_ATK && io.def_action_dev != nullptr);
+    const bool device_opponent = (KIND != TD_KIND_2P) && p.opponent_seeded && p.mt != nullptr && !host_opponent;
     // the record and the inputs are requested together: one round trip
     issue_env_load(w, rec);
     long long in_def = 0;
     long long atk_mine[TD_ROADS] = {TD_NTYPES, TD_NTYPES, TD_NTYPES};      // lanes 0..7 hold road i's cluster slots
     int in_opp = 0xff;
     if (KIND != TD_KIND_ATK && !MULTI) in_def = io.def_action_dev[env];
+    if (KIND == TD_KIND_ATK && io.def_action_dev != nullptr) in_def = io.def_action_dev[env];     // host-resolved build
+    unsigned in_cluster = 0xffffffffu;
+    if (KIND == TD_KIND_DEF && io.opponent_cluster_dev != nullptr) in_cluster = io.opponent_cluster_dev[env];
     if (KIND != TD_KIND_DEF && lane < TD_CLUSTER) {
 #pragma unroll
         for (int i = 0; i < TD_ROADS; ++i)
@@ -1544,10 +1604,18 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
                 summon_uniform(w, o & 3, min((o >> 4) & 3, w.mh()->num_roads - 1));
                 w.atk_cd = cc.atk_interval;
             }
-        } else if (device_opponent) opponent_enemy(w, p.difficulty);
+        } else if (io.opponent_cluster_dev != nullptr) {
+            if (in_cluster != 0xffffffffu) opponent_enemy(w, 0, in_cluster);
+        } else if (device_opponent) opponent_enemy(w, p.difficulty, 0xffffffffu);
     } else if (KIND == TD_KIND_ATK) {
         attacker();
-        if (device_opponent) opponent_tower(w, p.difficulty, dirty);
+        if (io.def_action_dev != nullptr) {                    // random_tower_lv0 resolved by the host (np_random)
+            const long long top = (long long)TD_NTYPES * w.ncells();
+            if (w.def_cd == 0 && in_def >= 0 && in_def < top) {
+                const int t = (int)(in_def / w.ncells()), loc = (int)(in_def - (long long)t * w.ncells());
+                if (tower_build(w, t, loc, dirty)) w.def_cd = cc.def_interval;
+            }
+        } else if (device_opponent) opponent_tower(w, p.difficulty, dirty);
     } else {
         attacker();
         defender();
@@ -1617,10 +1685,36 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
         for (int i = 0; i < TD_ROADS; ++i)
             io.real_atk_dev[(size_t)env * TD_ROADS * TD_CLUSTER + i * TD_CLUSTER + lane] = atk_mine[i];
     }
+    if (io.packed_out_dev != nullptr) {
+        // every small output of the env in one record and one coalesced store (the buffer may be host memory)
+        constexpr int kStride = KIND == TD_KIND_DEF ? 32 : 256;
+        int4 *po = reinterpret_cast<int4 *>(static_cast<uint8_t *>(io.packed_out_dev) + (size_t)env * kStride);
+        const long long rd = (MULTI || KIND == TD_KIND_ATK) ? 0ll : real_def;
+        const long long rbits = __double_as_longlong(reward);
+        const int win_v = done ? (my_win ? 1 : 0) : -1;
+        const unsigned fl = (done ? 1u : 0u) | ((unsigned)(win_v & 0xff) << 8) |
+                            ((unsigned)((w.def_cd <= 1 ? 1 : 0) | (w.atk_cd <= 1 ? 2 : 0)) << 16);
+        int4 v = make_int4(0, 0, 0, 0);
+        if (lane == 0) v = make_int4((int)rbits, (int)(rbits >> 32), (int)rd, (int)(rd >> 32));
+        if (lane == 1) v = make_int4((MULTI || KIND == TD_KIND_ATK) ? 0 : fail_def, (int)fl, 0, 0);
+        if (KIND != TD_KIND_DEF) {
+            if (lane == 2) v = make_int4(n_fail_atk, fail_atk[0], fail_atk[1], fail_atk[2]);
+            // lanes 4..15 carry real_atk[2q], real_atk[2q + 1] (q = lane - 4): slots k0, k0 + 1 of road q / 4
+            const int q = (lane - 4) & 15, k0 = (q & 3) * 2, road = q >> 2;
+            long long a0 = 0, a1 = 0;
+#pragma unroll
+            for (int i = 0; i < TD_ROADS; ++i) {
+                const long long x0 = gshfl(w, atk_mine[i], k0), x1 = gshfl(w, atk_mine[i], k0 + 1);
+                if (road == i) { a0 = x0; a1 = x1; }
+            }
+            if (lane >= 4 && lane < 16) v = make_int4((int)a0, (int)(a0 >> 32), (int)a1, (int)(a1 >> 32));
+        }
+        if (lane < kStride / 16) po[lane] = v;
+    }
     (void)def_ok;
     gsync(w);
 
-    if (done && io.auto_reset) {
+    if (__builtin_expect(done && io.auto_reset, 0)) {
         int next = (w.hdr()->map_id + p.map_stride) % p.n_maps;
         if (lane == 0) w.hdr()->episode += 1;
         reset_env(w, p, next, true);
@@ -1632,7 +1726,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
 // INC: the observation is an in-place update of the previous one (td_step_io.obs_incremental, vouched for by the
 // engine); a separate instantiation, so that the full-write kernels carry none of its code.
 template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, KIND == TD_KIND_ATK ? TD_MIN_BLOCKS_ATK : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);

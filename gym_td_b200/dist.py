@@ -8,16 +8,19 @@ import torch
 STAT_KEYS = ["return_sum", "episodes", "length_sum", "wins", "kills", "leaks", "steps"]
 
 
-def shard_range(n_global, rank, world):
-    """Contiguous env index range [lo, hi) of `rank`; ranges differ in size by at most one."""
-    base, rem = divmod(int(n_global), int(world))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
+RANK_STRIDE = 1_000_000      # env i of GPU g uses seed 1_000_000 * g + i
 
 
-def env_seeds(seed, lo, hi):
-    """Global seeding rule: the env with global index g uses seed + g for its map search and its opponent."""
-    return [(int(seed) + g) & 0xFFFFFFFF for g in range(lo, hi)]
+def rank_env_offset(rank):
+    """Global index of a rank's first env: the `env_offset` its TDVecEnv is created with.  Env i of rank r has the
+    global index g = RANK_STRIDE * r + i; map seeds and opponent generators derive from seed + g, so a rank's
+    results depend on its own global indices only -- never on the world size (bench.py, examples/rollout_feed.py)."""
+    return RANK_STRIDE * int(rank)
+
+
+def global_env_indices(rank, n_envs):
+    lo = rank_env_offset(rank)
+    return range(lo, lo + int(n_envs))
 
 
 def reduce_stats(stats, device="cpu"):

@@ -17,6 +17,7 @@ NT, NLV, CLUSTER, ROADS, NCH, MAX_L = 4, 2, 8, 3, 45, 64
 CAP_TOWERS, CAP_ENEMIES = 32, 64
 KIND_DEF, KIND_ATK, KIND_2P = 0, 1, 2
 KINDS = {"def": KIND_DEF, "atk": KIND_ATK, "2p": KIND_2P}
+OPTIONS = {"host_chunks": 1, "host_graph": 2, "step_smem_kb": 3, "obs_smem_kb": 4}
 
 _TABLES_F64 = ["enemy_LP", "enemy_speed", "enemy_defense", "enemy_cost", "tower_attack", "tower_cost",
                "tower_attack_interval"]
@@ -47,13 +48,15 @@ class TdStepIO(C.Structure):
                 ("obs_dev", C.c_void_p), ("reward_dev", C.c_void_p), ("done_dev", C.c_void_p),
                 ("win_dev", C.c_void_p), ("allow_next_dev", C.c_void_p), ("real_def_dev", C.c_void_p),
                 ("real_atk_dev", C.c_void_p), ("fail_def_dev", C.c_void_p), ("fail_atk_dev", C.c_void_p),
-                ("obs_incremental", C.c_int32), ("reserved_", C.c_int32)]
+                ("obs_incremental", C.c_int32), ("reserved_", C.c_int32), ("opponent_cluster_dev", C.c_void_p),
+                ("packed_out_dev", C.c_void_p)]
 
 
 class TdHostIO(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "def_action_host", "atk_action_host", "opponent_host", "obs_host", "reward_host", "done_host",
-        "win_host", "allow_next_host", "real_def_host", "real_atk_host", "fail_def_host", "fail_atk_host")]
+        "win_host", "allow_next_host", "real_def_host", "real_atk_host", "fail_def_host", "fail_atk_host",
+        "opponent_cluster_host", "packed_host")]
 
 
 class TdLayout(C.Structure):
@@ -91,7 +94,7 @@ EXPORTS = ["td_abi_version", "td_last_error", "td_default_config", "td_mapgen", 
            "td_destroy", "td_set_config", "td_get_layout", "td_upload_maps", "td_set_map_stride", "td_reset",
            "td_seed_opponent", "td_set_difficulty", "td_step", "td_observe", "td_step_host", "td_get_state",
            "td_set_state", "td_get_opponent", "td_get_stats", "td_reset_stats", "td_rollout_mask", "td_rollout_record",
-           "td_gae", "td_snapshot", "td_observe_snapshot"]
+           "td_gae", "td_snapshot", "td_observe_snapshot", "td_set_option", "td_packed_stride", "td_invalidate_obs"]
 
 
 def lib():
@@ -133,7 +136,9 @@ def lib():
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.td_gae.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double,
                              C.c_void_p, C.c_void_p, C.c_void_p]
-        if L.td_abi_version() != 2:
+        L.td_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.td_invalidate_obs.argtypes = [C.c_void_p]
+        if L.td_abi_version() != 3:
             raise ImportError("libtd_b200.so ABI version mismatch")
         _lib = L
     return _lib
@@ -242,6 +247,10 @@ class Engine(object):
     def set_map_stride(self, stride):
         self._check(self._lib.td_set_map_stride(self._h, int(stride)))
 
+    def set_option(self, option, value):
+        """Tuning knobs of the handle (TD_OPT_* of td_b200.h): "host_chunks", "host_graph", "step_smem_kb", "obs_smem_kb"."""
+        self._check(self._lib.td_set_option(self._h, OPTIONS[option] if isinstance(option, str) else int(option), int(value)))
+
     def set_difficulty(self, difficulty):
         self._check(self._lib.td_set_difficulty(self._h, int(difficulty)))
 
@@ -269,8 +278,10 @@ class Engine(object):
     @staticmethod
     def make_io(def_action=None, atk_action=None, opponent=None, multi_action=False, auto_reset=False, obs=None,
                 reward=None, done=None, win=None, allow_next=None, real_def=None, real_atk=None, fail_def=None,
-                fail_atk=None, obs_incremental=False):
+                fail_atk=None, obs_incremental=False, opponent_cluster=None, packed_out=None):
         io = TdStepIO()
+        io.packed_out_dev = _ptr(packed_out)
+        io.opponent_cluster_dev = _ptr(opponent_cluster)
         io.obs_incremental = int(bool(obs_incremental))
         io.def_action_dev, io.atk_action_dev, io.opponent_dev = _ptr(def_action), _ptr(atk_action), _ptr(opponent)
         io.multi_action, io.auto_reset = int(bool(multi_action)), int(bool(auto_reset))
@@ -284,6 +295,9 @@ class Engine(object):
 
     def step_host(self, io, host_io, stream=0):
         self._check(self._lib.td_step_host(self._h, C.byref(io), C.byref(host_io), stream))
+
+    def invalidate_obs(self):
+        self._check(self._lib.td_invalidate_obs(self._h))
 
     def observe(self, obs, stream=0):
         self._check(self._lib.td_observe(self._h, _ptr(obs), stream))

@@ -15,8 +15,10 @@ step and installs the advanced state afterwards, so `random.seed(s)` replays bit
 
 Deviations (documented): an invalid map draw (the reference raises or hangs) is retried
 from the same stream; multi-action mode returns FailCode 0 / [] where the reference raises;
-`random_agent=False` is available for the defender env at difficulty 1 only (the reference's other
-np_random paths raise); `render` is out of scope.
+`random_agent=False` (the scripted opponent on the env's own `np_random`) covers what the reference can run:
+TDDefense at difficulty 0 and 1, TDAttack at difficulty 0 (its lv1/lv2 np_random paths raise in the reference the
+first time the destruct gate opens, TDGymBasic.py:191,287); the draws are made on the host from the live
+`np_random` object and handed to the step as resolved opponent words.  `render` is out of scope.
 """
 import random
 
@@ -160,14 +162,15 @@ class TDGymBasic(object):
     def _multi(self):
         return bool(hyper_parameters.allow_multiple_actions)
 
-    def _launch(self, def_action=None, atk_action=None, opponent=None, real_def=None, scripted=False):
+    def _launch(self, def_action=None, atk_action=None, opponent=None, real_def=None, scripted=False,
+                opponent_cluster=None):
         """One device step.  `scripted`: the on-device opponent runs on Python's global `random` stream."""
         if scripted:
             st = random.getstate()
             self._engine.seed_opponent(np.asarray(st[1], dtype=np.uint64).astype(np.uint32).reshape(1, 625))
         o = self._out
         io = E.Engine.make_io(def_action=def_action, atk_action=atk_action, opponent=opponent,
-                              multi_action=self._multi() and self._kind != "atk", auto_reset=False, obs=self._obs,
+                              opponent_cluster=opponent_cluster, multi_action=self._multi() and self._kind != "atk", auto_reset=False, obs=self._obs,
                               reward=o["reward"], done=o["done"], win=o["win"], allow_next=o["allow"],
                               real_def=real_def, real_atk=o["real_atk"], fail_def=o["fail_def"],
                               fail_atk=o["fail_atk"])
@@ -180,6 +183,10 @@ class TDGymBasic(object):
     def _sync_cds(self):
         h = self._engine.decode_state(self._engine.get_state_raw(0, 1)[0])["header"]
         self.attacker_cd, self.defender_cd = int(h["attacker_cd"]), int(h["defender_cd"])
+        if int(h["flags"]):
+            # more live enemies / towers than the device lists hold (only reachable through paramConfig overrides):
+            # entries were dropped, the trajectory no longer follows the reference -- never silently
+            raise E.TdError(-5, "tower / enemy capacity exceeded (flags=%d): the episode is invalid" % int(h["flags"]))
 
     def _win(self):
         w = int(self._out["win"][0])
@@ -227,9 +234,7 @@ class TDDefense(TDGymBasic):
         if self.random_agent:
             self._engine.set_difficulty(self.difficulty)
             self._launch(def_action=d, real_def=real, scripted=True)
-        else:
-            if self.difficulty != 1:
-                raise NotImplementedError("random_agent=False is supported at difficulty 1 only")
+        elif self.difficulty == 1:
             byte = 0xFF
             if max(self.attacker_cd - 1, 0) == 0:                      # TDGymBasic.py:96,102-103
                 t = int(self.np_random.randint(0, config.enemy_types))
@@ -237,6 +242,15 @@ class TDDefense(TDGymBasic):
                 byte = t | (road << 4)
             opponent = torch.tensor([byte], dtype=torch.uint8, device=dev)
             self._launch(def_action=d, real_def=real, opponent=opponent)
+        else:
+            word = 0xFFFFFFFF
+            if max(self.attacker_cd - 1, 0) == 0:                      # TDGymBasic.py:82,87-89
+                cluster = self.np_random.randint(0, config.enemy_types, [hyper_parameters.max_cluster_length],
+                                                 dtype=np.int64)
+                road = int(self.np_random.randint(self.num_roads))
+                word = sum(int(c) << (2 * k) for k, c in enumerate(cluster)) | (road << 16)
+            cl = torch.tensor([word], dtype=torch.int64, device=dev).to(torch.uint32)
+            self._launch(def_action=d, real_def=real, opponent_cluster=cl)
         self._sync_cds()
         o = self._out
         done = bool(o["done"][0])
@@ -258,9 +272,9 @@ class TDAttack(TDGymBasic):
                                        dtype=np.int64)
         if difficulty not in (0, 1, 2):
             raise AttributeError("'TDAttack' object has no attribute 'random_tower_lv%s'" % (difficulty,))
-        if not random_agent:
-            raise NotImplementedError("TDAttack(random_agent=False) raises in the reference (TDGymBasic.py:191); "
-                                      "use random_agent=True and random.seed()")
+        if not random_agent and difficulty != 0:
+            raise NotImplementedError("TDAttack(random_agent=False) at difficulty 1 / 2 raises in the reference "
+                                      "(TDGymBasic.py:191,287); use random_agent=True and random.seed()")
         self.difficulty = difficulty
         self.name = "TDAttack"
 
@@ -271,8 +285,17 @@ class TDAttack(TDGymBasic):
         err_msg = "%r (%s) invalid" % (action, type(action))
         assert self.action_space.contains(action), err_msg
         a = _as_device_action(action, (1, 3, 8), self._device)
-        self._engine.set_difficulty(self.difficulty)
-        self._launch(atk_action=a, scripted=True)
+        if self.random_agent:
+            self._engine.set_difficulty(self.difficulty)
+            self._launch(atk_action=a, scripted=True)
+        else:
+            build = -1
+            if max(self.defender_cd - 1, 0) == 0:                      # TDGymBasic.py:112,118-119
+                r, c = self.np_random.randint(0, self.map_size, [2, ])
+                t = int(self.np_random.randint(0, config.tower_types))
+                build = t * self.map_size * self.map_size + int(r) * self.map_size + int(c)
+            b = torch.tensor([build], dtype=torch.int64, device=self._device)
+            self._launch(atk_action=a, def_action=b)
         self._sync_cds()
         o = self._out
         fa = o["fail_atk"][0].tolist()

@@ -84,7 +84,7 @@ class TDVecEnv(object):
             self.engine.set_difficulty(difficulty)
             self.engine.seed_opponent_python((np.arange(num_envs, dtype=np.uint64) + base).astype(np.uint32))
         N, L, dev = self.num_envs, self.map_size, self.device
-        self.obs = torch.empty((N, E.NCH, L, L), dtype=torch.float32, device=dev)
+        self._obs = torch.empty((N, E.NCH, L, L), dtype=torch.float32, device=dev)
         # the small per-step outputs live in one slab (mirrored by one pinned host slab in step_host, so that
         # td_step_host moves them with a single device->host copy)
         self._layout, off = {}, 0
@@ -110,6 +110,24 @@ class TDVecEnv(object):
         self._host = None
         self._io_cache = None
         self._hio_cache = None
+
+    # `obs` is the tensor every step writes.  Rebinding it (env.obs = other) is allowed; the in-place observation
+    # update (incremental_obs) then starts over with a full write, also when the new tensor reuses the old address.
+    @property
+    def obs(self):
+        return self._obs
+
+    @obs.setter
+    def obs(self, t):
+        N, L = self.num_envs, self.map_size
+        if tuple(t.shape) != (N, E.NCH, L, L) or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("obs must be a contiguous CUDA float32 tensor of shape %r" % ((N, E.NCH, L, L),))
+        self._obs = t
+        self.engine.invalidate_obs()
+
+    def invalidate_obs(self):
+        """Call after writing into `env.obs` yourself while incremental_obs is on."""
+        self.engine.invalidate_obs()
 
     # -- spaces-like metadata -------------------------------------------------------------------
     @property
@@ -182,19 +200,34 @@ class TDVecEnv(object):
 
     # -- host-buffer path (what a numpy-facing gym caller uses) ------------------------------------
     def _host_buffers(self):
+        """Page-locked host side of step_host.  The small outputs arrive as one packed record per env
+        (td_step_packed, 32 B for TD-def, 256 B otherwise) that the step kernel stores straight into this
+        buffer -- no device->host copy; the dict exposes the fields as (strided) views of it."""
         if self._host is None:
-            slab = torch.empty(self._slab.shape, dtype=torch.uint8).pin_memory()
-            v = lambda k: self._view(slab, k) if k in self._layout else None
-            h = dict(reward=v("reward"), done=v("done"), win=v("win"), allow=v("allow"), fail_def=v("fail_def"),
-                     fail_atk=v("fail_atk"), real_atk=v("real_atk"), real_def=v("real_def"), obs=None, slab=slab)
+            N = self.num_envs
+            stride = 32 if self.kind == "def" else 256
+            packed = torch.zeros((N, stride), dtype=torch.uint8).pin_memory()
+            f = lambda lo, hi, dt: packed[:, lo:hi].view(dt)
+            h = dict(packed=packed, reward=f(0, 8, torch.float64)[:, 0], done=packed[:, 20], win=f(21, 22, torch.int8)[:, 0],
+                     allow=packed[:, 22], real_def=None, fail_def=None, real_atk=None, fail_atk=None, obs=None)
+            if self.kind != "atk":
+                h["fail_def"] = f(16, 20, torch.int32)[:, 0]
+                if not self.multi_action:
+                    h["real_def"] = f(8, 16, torch.int64)[:, 0]
+                else:                                  # [N, 6, L, L]: too large for the record, copied on request
+                    h["real_def"] = torch.empty(self.real_def.shape, dtype=torch.int64).pin_memory()
+            if self.kind != "def":
+                h["fail_atk"] = f(32, 48, torch.int32)
+                h["real_atk"] = f(64, 256, torch.int64).view(N, E.ROADS, E.CLUSTER)
             h["def_dev"] = torch.zeros_like(self.real_def) if self.real_def is not None else None
             h["atk_dev"] = torch.zeros_like(self.real_atk) if self.real_atk is not None else None
             self._host = h
         return self._host
 
     def step_host(self, action, want_obs=False):
-        """Host in, host out through td_step_host: `action` are pinned CPU int64 tensors; the small outputs
-        (and the observation when want_obs) are copied back and the stream is synchronised."""
+        """Host in, host out through td_step_host: `action` are pinned CPU int64 tensors; the small outputs land
+        in pinned host memory while the kernel runs (and the observation is copied when want_obs); the stream
+        is synchronised before the call returns.  Returns a dict of host tensors (views, valid until the next call)."""
         h = self._host_buffers()
         d, a = self._split(action)
         if want_obs and h["obs"] is None:
@@ -203,12 +236,9 @@ class TDVecEnv(object):
         hio = self._hio_cache
         if hio is None:
             hio = self._hio_cache = E.TdHostIO()
-            hio.reward_host, hio.done_host, hio.win_host = h["reward"].data_ptr(), h["done"].data_ptr(), h["win"].data_ptr()
-            hio.allow_next_host = h["allow"].data_ptr()
-            if self.kind != "atk":
-                hio.real_def_host, hio.fail_def_host = h["real_def"].data_ptr(), h["fail_def"].data_ptr()
-            if self.kind != "def":
-                hio.real_atk_host, hio.fail_atk_host = h["real_atk"].data_ptr(), h["fail_atk"].data_ptr()
+            hio.packed_host = h["packed"].data_ptr()
+            if self.kind != "atk" and self.multi_action:
+                hio.real_def_host = h["real_def"].data_ptr()
         hio.def_action_host = d.data_ptr() if d is not None else None
         hio.atk_action_host = a.data_ptr() if a is not None else None
         hio.obs_host = h["obs"].data_ptr() if want_obs else None
@@ -222,11 +252,9 @@ class TDVecEnv(object):
             h2d += self.real_def.numel() * 8
         if self.kind != "def":
             h2d += N * 24 * 8
-        d2h = N * (8 + 1 + 1 + 1)
-        if self.kind != "atk":
-            d2h += self.real_def.numel() * 8 + N * 4
-        if self.kind != "def":
-            d2h += N * 24 * 8 + N * 16
+        d2h = N * (32 if self.kind == "def" else 256)          # packed records, written by the kernel itself
+        if self.kind != "atk" and self.multi_action:
+            d2h += self.real_def.numel() * 8
         if want_obs:
             d2h += N * E.NCH * L * L * 4
         return h2d, d2h

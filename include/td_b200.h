@@ -39,7 +39,8 @@
 extern "C" {
 #endif
 
-#define TD_ABI_VERSION 2   /* 2: td_step_io grew `obs_incremental` (+ reserved_) at its end */
+#define TD_ABI_VERSION 3   /* 2: td_step_io grew `obs_incremental` (+ reserved_) at its end; 3: td_set_option,
+                              config per handle, td_step_host as one graph launch */
 
 enum { TD_OK = 0, TD_E_INVALID = -1, TD_E_CUDA = -2, TD_E_ALLOC = -3, TD_E_STATE = -4,
        TD_E_OVERFLOW = -5 };
@@ -104,7 +105,10 @@ typedef struct td_handle td_handle;
 /* Per-step device buffers.  Unused pointers may be NULL.  Leading dimension is n_envs. */
 typedef struct td_step_io {
     /* inputs */
-    const int64_t *def_action_dev;   /* DEF/2P: [n] Discrete, or [n,6,L,L] when multi_action != 0 */
+    const int64_t *def_action_dev;   /* DEF/2P: [n] Discrete, or [n,6,L,L] when multi_action != 0.
+                                        ATK: optional host-resolved scripted defender (random_tower_lv0 on the env's
+                                        np_random, TDGymBasic.py:117-121): [n] build actions type * L*L + r*L + c,
+                                        < 0 = defender does nothing; NULL = the on-device scripted defender */
     const int64_t *atk_action_dev;   /* ATK/2P: [n,3,8] */
     const uint8_t *opponent_dev;     /* DEF only, optional host-resolved scripted attacker (random_enemy_lv1):
                                         [n] bytes, type | road<<4, 0xFF = attacker does nothing.  When NULL the
@@ -133,7 +137,32 @@ typedef struct td_step_io {
                                         td_set_state, for envs that were reset inside the step, for board sizes
                                         without a specialised kernel. */
     int32_t reserved_;
+    /* more inputs (ABI 3) */
+    const uint32_t *opponent_cluster_dev; /* DEF only, optional host-resolved scripted attacker with a free cluster
+                                        (random_enemy_lv0 on the env's np_random, TDGymBasic.py:87-89): [n] words,
+                                        bits 2k..2k+1 = enemy type of slot k (k < 8), bits 16-17 = road,
+                                        0xFFFFFFFF = attacker does nothing.  Takes the place of opponent_dev. */
+    void *packed_out_dev;            /* optional: [n] td_step_packed records (td_packed_stride bytes apart), every
+                                        small per-step output of an env in ONE coalesced store.  May be page-locked
+                                        HOST memory (device-accessible under UVA): the outputs then reach the host
+                                        while the kernel runs.  Written in addition to the arrays above. */
 } td_step_io;
+
+/* One env's small outputs in one record.  DEF envs use the first 32 bytes (stride 32), ATK / 2P envs all 256. */
+typedef struct td_step_packed {
+    double reward;
+    int64_t real_def;                /* Discrete RealAction (0 in multi_action mode: see real_def_dev) */
+    int32_t fail_def;
+    uint8_t done;
+    int8_t win;
+    uint8_t allow_next;
+    uint8_t pad0_;
+    int32_t pad1_[2];                /* -- 32 bytes: end of a DEF record */
+    int32_t fail_atk[4];
+    int32_t pad2_[4];
+    int64_t real_atk[TD_ROADS * TD_CLUSTER];
+} td_step_packed;                    /* 256 bytes */
+int td_packed_stride(int env_kind);   /* 32 for TD_KIND_DEF, 256 otherwise */
 
 /* byte offsets inside one env record, for td_get_state / td_set_state blobs */
 typedef struct td_layout {
@@ -236,6 +265,9 @@ int td_seed_opponent_python(td_handle *h, const uint32_t *seeds_host, int first_
 int td_set_difficulty(td_handle *h, int difficulty);
 
 int td_step(td_handle *h, const td_step_io *io, void *stream);
+/* obs_incremental bookkeeping: the library remembers the ADDRESS of the buffer it filled last.  If that memory was
+ * freed and re-allocated, or written by anybody else, call this before the next step: it then writes all planes. */
+int td_invalidate_obs(td_handle *h);
 /* observation of the current state only (kernel (f) alone) */
 int td_observe(td_handle *h, float *obs_dev, void *stream);
 
@@ -255,8 +287,22 @@ typedef struct td_host_io {
     int64_t *real_atk_host;
     int32_t *fail_def_host;
     int32_t *fail_atk_host;
+    const uint32_t *opponent_cluster_host;   /* ABI 3: host side of td_step_io.opponent_cluster_dev */
+    void *packed_host;               /* ABI 3: page-locked [n] td_step_packed records.  The step kernel writes them
+                                        directly (zero-copy); leave the per-field host pointers above NULL and
+                                        td_step_host issues no device->host copy at all. */
 } td_host_io;
 int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, void *stream);
+/* td_step_host runs as ONE CUDA-graph launch per call (copies in, the step kernels of 1..n chained chunks of the
+ * batch, copies out), cached per distinct set of buffers; with pageable host memory, or TD_OPT_HOST_GRAPH = 0, the
+ * same operations are issued on the stream one by one.  Passing the legacy default stream (NULL) is fine. */
+
+/* tuning knobs of a handle (no environment variables are read anywhere in the library) */
+enum { TD_OPT_HOST_CHUNKS = 1,   /* td_step_host: chunks the batch is cut into; 0 = automatic */
+       TD_OPT_HOST_GRAPH = 2,    /* td_step_host: 1 = graph launch (default), 0 = plain stream launches */
+       TD_OPT_STEP_SMEM_KB = 3,  /* experiments: minimum dynamic shared memory of a step CTA (lowers residency) */
+       TD_OPT_OBS_SMEM_KB = 4 }; /* experiments: the same for td_observe */
+int td_set_option(td_handle *h, int option, int value);
 
 /* raw env records (td_layout) to/from host; blob is n * record_bytes */
 int td_get_state(td_handle *h, int first_env, int n, void *blob_host);
@@ -289,6 +335,7 @@ int td_rollout_record(td_handle *h, int which, const int64_t *action_dev, const 
                       float *rewards_row_dev, uint8_t *dones_row_dev, int64_t *actions_row_dev, void *stream);
 int td_gae(int horizon, int n, const float *rewards_dev, const uint8_t *dones_dev, const float *values_dev,
            const float *next_value_dev, double gamma, double lam, float *advs_dev, float *returns_dev, void *stream);
+/* td_gae takes no handle: it runs on the device that owns rewards_dev (made current for the calling thread). */
 
 #ifdef __cplusplus
 }

@@ -247,12 +247,24 @@ def extra():
            tag="atk_L20_override_c")
 
 
+def extra2():
+    """Third batch (python -m oracle.make_golden --extra2): the scripted opponents on the env's own np_random
+    (random_agent=False) that the reference can run -- random_enemy_lv0, random_tower_lv0 -- and the multi-action
+    defender against the np_random attacker."""
+    record("def", 10, 610, 600, difficulty=0, random_agent=False)
+    record("atk", 10, 620, 600, difficulty=0, random_agent=False)
+    record("def", 20, 630, 300, multi=True, random_agent=False)
+
+
 def main():
     ref_loader.load()
     np.seterr(all="ignore")
     os.makedirs(OUT, exist_ok=True)
     if "--extra" in sys.argv:
         extra()
+        return 0
+    if "--extra2" in sys.argv:
+        extra2()
         return 0
     reference_selftest()
     survey_kats()

@@ -1,4 +1,4 @@
-"""Subprocess body of test_gpu_env.py::test_chunked_host_path_equals_device_path (needs TD_HOST_CHUNKS in env)."""
+"""Subprocess body of test_gpu_env.py::test_chunked_host_path_equals_device_path: argv = chunks, graph (0/1)."""
 import os
 import sys
 
@@ -13,6 +13,8 @@ def main():
         b = TDVecEnv(kind, L, N, seed=9, auto_reset=True)
         a.reset()
         b.reset()
+        b.engine.set_option("host_chunks", int(sys.argv[1]))
+        b.engine.set_option("host_graph", int(sys.argv[2]))
         g = torch.Generator(device="cuda").manual_seed(1)
         for t in range(60):
             d = torch.randint(0, 6 * L * L + 1, (N,), device="cuda", generator=g)
@@ -35,7 +37,7 @@ def main():
                 assert torch.equal(h["obs"].view(torch.int32), obs.cpu().view(torch.int32))
         a.close()
         b.close()
-    print("chunked host path ok", os.environ.get("TD_HOST_CHUNKS"))
+    print("chunked host path ok", sys.argv[1:])
 
 
 if __name__ == "__main__":

@@ -326,4 +326,29 @@ def _def_stream(o, action, byte):
 
 
 def _def_multi_stream(o, action, byte):
-    raise NotImplementedError
+    """TDDefense.step in multi-action mode (TDDefense.py:40-60) with the scripted attacker's (type, road) supplied
+    by the caller: the wrapper restated over the oracle's board calls, flagged cells in r-major / c / channel order."""
+    e = o.e
+    e.attacker_cd = max(e.attacker_cd - 1, 0)
+    e.defender_cd = max(e.defender_cd - 1, 0)
+    L = e.L
+    out = o.out
+    C.memset(C.byref(out), 0, C.sizeof(out))
+    out.win, out.win_attacker = -1, -1
+    real = np.zeros((6, L, L), dtype=np.int64)
+    if e.defender_cd == 0:
+        flagged = np.argwhere(np.transpose(action, (1, 2, 0)) == 1)          # sorted by (r, c, channel)
+        for r, c, ch in flagged:
+            loc = int(r) * L + int(c)
+            ok = o.tower_build(int(ch), loc) if ch < 4 else (o.tower_lvup(loc) if ch == 4 else o.tower_destruct(loc))
+            if ok:
+                e.defender_cd = o.cfg.defender_action_interval
+                real[ch, r, c] = 1
+    _opp_cluster(o, int(byte))
+    out.reward = o.board_step()
+    out.done = int(o.done())
+    if out.done:
+        out.win = 1 if (not e.has_base_LP or e.base_LP > 0) else 0
+    out.allow_next_def = int(e.defender_cd <= 1)
+    out.allow_next_atk = int(e.attacker_cd <= 1)
+    return out, real

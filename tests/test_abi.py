@@ -25,7 +25,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), "libtd_b200.so lacks %s" % n
     assert sorted(E.EXPORTS) == names
-    assert lib.td_abi_version() == 2
+    assert lib.td_abi_version() == 3
 
 
 def test_struct_sizes_match_header():
@@ -106,9 +106,7 @@ def test_no_cpu_fallback():
         gym_td_b200.make("TD-def-small-v0", seed=1)
 
 
-def test_plain_c_program_against_the_library(tmp_path):
-    """examples/c_abi_demo.c: the boundary used from C alone.  Host-only entry points work everywhere; td_create
-    reports TD_E_CUDA with a message on a box without a GPU (exit code 3) and the demo runs through on one."""
+def _run_c_demo(tmp_path):
     import subprocess
     E.lib()                                                   # builds the library if needed
     cuda = "/usr/local/cuda"
@@ -120,9 +118,24 @@ def test_plain_c_program_against_the_library(tmp_path):
                            os.path.join(ROOT, "examples", "c_abi_demo.c"), "-L", libdir, "-ltd_b200",
                            "-Wl,-rpath," + libdir, "-L", os.path.join(cuda, "lib64"), "-lcudart"])
     res = subprocess.run([str(exe), "256", "20"], capture_output=True, text=True, timeout=300)
-    assert "ABI version 2" in res.stdout and "road(s)" in res.stdout
+    assert "ABI version 3" in res.stdout and "road(s)" in res.stdout
+    return res
+
+
+def test_plain_c_program_against_the_library(tmp_path):
+    """examples/c_abi_demo.c: the boundary used from C alone.  Host-only entry points work everywhere; td_create
+    reports TD_E_CUDA with a message on a box without a GPU (exit code 3) and the demo runs through on one."""
+    res = _run_c_demo(tmp_path)
     assert res.returncode in (0, 3), res.stdout + res.stderr
     if res.returncode == 3:
         assert "no CPU fallback" in res.stdout
     else:
         assert "env-steps" in res.stdout
+
+
+@pytest.mark.gpu
+def test_plain_c_program_steps_envs_on_the_gpu(tmp_path):
+    """The same C program on a GPU box: create, upload maps, reset, step, read statistics -- from C alone."""
+    res = _run_c_demo(tmp_path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "env-steps" in res.stdout

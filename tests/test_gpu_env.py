@@ -107,6 +107,48 @@ def test_facade_against_live_reference():
         mine.close()
 
 
+@pytest.mark.parametrize("kind,difficulty", [("def", 0), ("def", 1), ("atk", 0)])
+def test_facade_np_random_opponents_against_live_reference(kind, difficulty):
+    """random_agent=False: the scripted opponent draws from the env's own np_random (TDGymBasic.py:87-89, 102-103,
+    117-119).  The facade resolves the draws on the host from the live RandomState and hands them to the kernel;
+    observations, rewards, info and the np_random stream itself must follow the reference step by step."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("reference not present on this box")
+    import gym_td_b200 as G
+    from oracle import ref_harness as RH
+    ref_loader.load()
+    np.seterr(all="ignore")
+    seed, ref = RH.first_valid_seed(kind, 10, 2040 + difficulty, difficulty=difficulty, random_agent=False)
+    cls = G.TDDefense if kind == "def" else G.TDAttack
+    mine = cls(10, difficulty=difficulty, seed=seed, random_agent=False)
+    assert np.array_equal(ref._board.get_states(), mine._board.get_states())
+    rs = np.random.RandomState(6)
+    for t in range(400):
+        a = RH.smart_defender_action(ref._board, rs) if kind == "def" else rs.randint(0, 5, size=(3, 8))
+        o1, r1, d1, i1 = ref.step(a)
+        o2, r2, d2, i2 = mine.step(a)
+        assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32)) and repr(r1) == repr(r2) and d1 == d2, t
+        assert np.array_equal(np.asarray(i1["RealAction"]), np.asarray(i2["RealAction"]))
+        assert json.dumps(i1["FailCode"], default=int) == json.dumps(i2["FailCode"], default=int)
+        assert i1["AllowNextMove"] == i2["AllowNextMove"] and repr(i1["Win"]) == repr(i2["Win"])
+        s1, s2 = ref.np_random.get_state(), mine.np_random.get_state()
+        assert s1[2] == s2[2] and np.array_equal(s1[1], s2[1]), "np_random streams diverged at step %d" % t
+        if d1:
+            break
+    assert t > 50
+    mine.close()
+
+
+def test_facade_refuses_what_the_reference_cannot_run():
+    import gym_td_b200 as G
+    for d in (1, 2):
+        with pytest.raises(NotImplementedError):
+            G.TDAttack(10, difficulty=d, seed=3, random_agent=False)
+    with pytest.raises(AttributeError):
+        G.TDDefense(10, difficulty=2, seed=3)
+
+
 def test_invalid_action_asserts_like_the_reference():
     import gym_td_b200 as G
     env = G.make("TD-def-small-v0", seed=5)
@@ -227,6 +269,47 @@ def test_capacity_overflow_is_flagged_not_silent():
     with pytest.raises(E.TdError):
         env.stats()
     env.close()
+
+
+def test_capacity_overflow_raises_in_the_facade_too():
+    """the n = 1 facades read the sticky overflow flags after every step."""
+    import gym_td_b200 as G
+    from gym_td_b200 import engine as E
+    kw = dict(enemy_cost=[[1, 1]] * 4, attacker_init_cost=100, base_LP=None, enemy_speed=[[.01, .01]] * 4)
+    old = {k: getattr(G.config, k) for k in kw}
+    G.paramConfig(**kw)
+    try:
+        env = G.make("TD-atk-small-v0", seed=1)
+        with pytest.raises(E.TdError):
+            for _ in range(12):
+                env.step(np.zeros((3, 8), dtype=np.int64))
+        env.close()
+    finally:
+        G.paramConfig(**old)
+
+
+def test_rebinding_obs_restarts_the_incremental_update():
+    """the in-place observation update trusts a buffer by address; TDVecEnv drops that trust whenever
+    `obs` is rebound, also to memory at the very same address."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    N, L = 64, 10
+    a = TDVecEnv("def", L, N, seed=3, auto_reset=True, incremental_obs=True)
+    b = TDVecEnv("def", L, N, seed=3, auto_reset=True)
+    a.reset(), b.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in range(60):
+        act = torch.randint(0, 601, (N,), device="cuda", generator=g)
+        if t == 20:
+            a.obs.fill_(7.0)                    # somebody scribbled over the buffer ...
+            a.obs = a.obs                       # ... and says so by rebinding (same address)
+        if t == 40:
+            a.obs.zero_()
+            a.invalidate_obs()
+        o1, _, _, _ = a.step(act)
+        o2, _, _, _ = b.step(act)
+        assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)), t
+    a.close(), b.close()
 
 
 def test_full_size_determinism_and_replayed_subset():
@@ -366,14 +449,14 @@ def test_checkpoint_resume_is_bit_identical(kind):
     env.close()
 
 
-@pytest.mark.parametrize("chunks", ["1", "3", "4"])
-def test_chunked_host_path_equals_device_path(chunks):
-    """td_step_host cuts large batches into chunks on two internal streams; results must not depend on it."""
+@pytest.mark.parametrize("chunks,graph", [("1", "1"), ("3", "1"), ("4", "1"), ("0", "1"), ("3", "0")])
+def test_chunked_host_path_equals_device_path(chunks, graph):
+    """td_step_host cuts the batch into chained chunks inside one CUDA graph (or plain stream launches); results must
+    not depend on the chunking, on the launch mode, or on which cached graph serves a call."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, TD_HOST_CHUNKS=chunks)
-    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_chunk_check.py")], env=env,
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_chunk_check.py"), chunks, graph],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert "chunked host path ok" in out.stdout

@@ -57,23 +57,41 @@ def test_cuda_replays_reference_trajectory(path):
                fail_def=torch.zeros(1, dtype=torch.int32, device=dev), fail_atk=torch.zeros((1, 4), dtype=torch.int32, device=dev),
                real_atk=torch.zeros((1, 3, 8), dtype=torch.int64, device=dev))
     real_def = torch.zeros((1, 6, L, L) if traj.multi else (1,), dtype=torch.int64, device=dev)
-    atk_cd = 0
+    atk_cd = def_cd = 0
+    diff = traj.meta["difficulty"]
     for t in range(1, traj.T + 1):
-        d = a = opp = None
+        d = a = opp = cluster = None
         if kind != "atk":
             d = torch.from_numpy(np.ascontiguousarray(traj.def_action(t)).reshape(real_def.shape)).to(dev)
         if kind != "def":
             a = torch.from_numpy(traj.atk_action(t).reshape(1, 3, 8)).to(dev)
-        if use_np:                       # host-resolved scripted attacker on the env's np_random stream
+        if use_np and kind == "def":     # host-resolved scripted attacker on the env's np_random stream
             atk_cd = max(atk_cd - 1, 0)
-            byte = 0xFF
+            byte, word = 0xFF, 0xFFFFFFFF
             if atk_cd == 0:
-                tt = int(np_rs.randint(0, 4))
-                rd = int(np_rs.randint(int(z["num_roads"])))
-                byte = tt | (rd << 4)
+                if diff == 1:                                           # TDGymBasic.py:102-103
+                    tt = int(np_rs.randint(0, 4))
+                    rd = int(np_rs.randint(int(z["num_roads"])))
+                    byte = tt | (rd << 4)
+                else:                                                   # TDGymBasic.py:87-89
+                    cl = np_rs.randint(0, 4, [8], dtype=np.int64)
+                    rd = int(np_rs.randint(int(z["num_roads"])))
+                    word = sum(int(c) << (2 * k) for k, c in enumerate(cl)) | (rd << 16)
                 atk_cd = cfg.attacker_action_interval
-            opp = torch.tensor([byte], dtype=torch.uint8, device=dev)
-        io = E.Engine.make_io(def_action=d, atk_action=a, opponent=opp, multi_action=traj.multi, obs=obs,
+            if diff == 1:
+                opp = torch.tensor([byte], dtype=torch.uint8, device=dev)
+            else:
+                cluster = torch.tensor([word], dtype=torch.int64, device=dev).to(torch.uint32)
+        if use_np and kind == "atk":     # random_tower_lv0 on np_random (TDGymBasic.py:112,118-121)
+            assert diff == 0
+            build = -1
+            if max(def_cd - 1, 0) == 0:
+                r, c = np_rs.randint(0, L, [2, ])
+                tt = int(np_rs.randint(0, 4))
+                build = tt * L * L + int(r) * L + int(c)
+            d = torch.tensor([build], dtype=torch.int64, device=dev)
+        io = E.Engine.make_io(def_action=d, atk_action=a, opponent=opp, opponent_cluster=cluster,
+                              multi_action=traj.multi, obs=obs,
                               reward=out["reward"], done=out["done"], win=out["win"], allow_next=out["allow"],
                               real_def=real_def, real_atk=out["real_atk"], fail_def=out["fail_def"],
                               fail_atk=out["fail_atk"])
@@ -85,5 +103,6 @@ def test_cuda_replays_reference_trajectory(path):
                          real_def[0].cpu().numpy() if traj.multi else None)
         assert GU.digest64(obs[0].cpu().numpy().tobytes()) == z["obs_digest"][t], "%s obs step %d" % (traj.name, t)
         sd = _state_dict(eng, eng.get_state_raw(0, 1)[0], base_none)
+        def_cd = sd["defender_cd"]
         assert GU.digest64(GU.state_bytes(sd)) == z["state_digest"][t - 1], "%s state step %d" % (traj.name, t)
     eng.close()

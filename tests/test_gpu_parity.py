@@ -21,6 +21,12 @@ def test_def_discrete_host_stream():
     assert PU.run_parity("def", 10, n_envs=32, steps=600, seed=3, opponent="stream") > 3000
 
 
+def test_def_multi_action_host_stream():
+    """TDDefense(random_agent=False) in allow_multiple_actions mode: Box defender + host-resolved attacker byte."""
+    assert PU.run_parity("def", 10, n_envs=16, steps=400, seed=13, multi=True, opponent="stream") > 1000
+    assert PU.run_parity("def", 20, n_envs=8, steps=150, seed=14, multi=True, opponent="stream", multi_mode="uniform") > 500
+
+
 @pytest.mark.parametrize("L", [10, 20, 30])
 def test_atk_device_opponent(L):
     assert PU.run_parity("atk", L, n_envs=32, steps=1200, seed=L + 2, opponent="device", difficulty=1) > 3000

@@ -109,6 +109,52 @@ def test_rollout_buffer_on_live_env_matches_oracle():
 
 
 @pytest.mark.gpu
+def test_rollout_buffers_for_both_players_of_the_2p_env():
+    """BASELINE config 5: TD-2p feeds one rollout buffer per player; each row equals the reference's bookkeeping
+    applied to that player's action / RealAction / AllowNextMove bit, the attacker on the negated reward."""
+    import torch
+    from gym_td_b200.rollout import RolloutBuffer
+    from gym_td_b200.vec_env import TDVecEnv
+    from tests import parity_util as PU
+    N, L, T = 256, 10, 24
+    env = TDVecEnv("2p", L, N, seed=12, auto_reset=True,
+                   cfg=PU.make_config(defender_action_interval=3, attacker_action_interval=2))
+    env.reset()
+    with pytest.raises(ValueError):
+        RolloutBuffer(env, horizon=T)
+    bd, ba = RolloutBuffer(env, horizon=T, role="defender"), RolloutBuffer(env, horizon=T, role="attacker")
+    g = torch.Generator(device="cuda").manual_seed(4)
+    allow_d, allow_a = np.ones(N, dtype=bool), np.ones(N, dtype=bool)
+    rows = {"d": [], "a": [], "done": []}
+    for t in range(T):
+        act = {"Defender": torch.randint(0, 601, (N,), dtype=torch.int64, device="cuda", generator=g),
+               "Attacker": torch.randint(0, 5, (N, 3, 8), dtype=torch.int64, device="cuda", generator=g)}
+        want_d = RO.mask_actions(act["Defender"].cpu().numpy(), allow_d, 600)
+        want_a = act["Attacker"].cpu().numpy().copy()
+        want_a[~allow_a] = 4
+        bd.mask(act), ba.mask(act)
+        assert np.array_equal(act["Defender"].cpu().numpy(), want_d) and np.array_equal(act["Attacker"].cpu().numpy(), want_a)
+        obs, rew, done, info = env.step(act)
+        bd.record(act), ba.record(act)
+        r, dn = rew.cpu().numpy(), done.cpu().numpy()
+        rows["d"].append(RO.record_row(want_d, info["RealAction"]["Defender"].cpu().numpy(), r, dn)[0])
+        rows["a"].append(RO.record_row(want_a, info["RealAction"]["Attacker"].cpu().numpy(), -r, dn)[0])
+        rows["done"].append(dn)
+        allow_d = info["AllowNextMove"]["Defender"].cpu().numpy()
+        allow_a = info["AllowNextMove"]["Attacker"].cpu().numpy()
+    assert np.array_equal(bd.rewards.cpu().numpy().view(np.uint32), np.stack(rows["d"]).view(np.uint32))
+    assert np.array_equal(ba.rewards.cpu().numpy().view(np.uint32), np.stack(rows["a"]).view(np.uint32))
+    assert np.array_equal(ba.dones.cpu().numpy().astype(bool), np.stack(rows["done"]))
+    values = torch.randn((T, N), device="cuda", generator=g)
+    nv = torch.randn((N,), device="cuda", generator=g)
+    advs, rets = ba.flush(-values, -nv)
+    a_ref, r_ref = RO.gae(np.stack(rows["a"]), np.stack(rows["done"]), (-values).cpu().numpy(), (-nv).cpu().numpy(), 0.99, 0.95)
+    assert np.array_equal(advs.cpu().numpy().view(np.uint32), a_ref.view(np.uint32))
+    assert np.array_equal(rets.cpu().numpy().view(np.uint32), r_ref.view(np.uint32))
+    env.close()
+
+
+@pytest.mark.gpu
 def test_policy_reads_observation_in_place():
     """BASELINE.json config 5 in miniature: dict actions sampled on the GPU, obs consumed in place."""
     import subprocess
