@@ -42,13 +42,12 @@ def test_spaces_contains_semantics():
     assert b.sample().shape == (3, 8)
 
 
-def test_shard_ranges_partition_the_envs():
-    for n, world in ((65536, 8), (10, 3), (7, 8)):
-        r = [dist.shard_range(n, k, world) for k in range(world)]
-        assert r[0][0] == 0 and r[-1][1] == n
-        assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
-        assert max(b - a for a, b in r) - min(b - a for a, b in r) <= 1
-    assert dist.env_seeds(5, 2, 5) == [7, 8, 9]
+def test_rank_env_ranges_are_disjoint():
+    """The sharding rule bench.py and examples/rollout_feed.py use: rank r owns global env indices
+    [1_000_000 r, 1_000_000 r + n), whatever the world size."""
+    ranges = [dist.global_env_indices(r, 65536) for r in range(8)]
+    assert [rg[0] for rg in ranges] == [1_000_000 * r for r in range(8)] == [dist.rank_env_offset(r) for r in range(8)]
+    assert all(a[-1] < b[0] for a, b in zip(ranges, ranges[1:]))
 
 
 def test_distance_plane_division_is_correctly_rounded_for_every_operand():
