@@ -18,7 +18,7 @@ struct td_handle {
     int device, kind, L, cells, cells_pad, n_envs;
     int n_maps, map_stride, difficulty;
     int record_bytes, map_bytes, smem_per_warp, scratch_off;
-    int old_lists_off;
+    int old_lists_off, act_stage_off;
     const float *obs_synced;       // buffer that holds the current observation of every env (NULL: none known)
     int off_static, off_towers, off_enemies, off_map6, rng_cache_words;
     uint8_t *records;
@@ -214,6 +214,7 @@ static void fill_params(const td_handle *h, StepParams &p)
     p.difficulty = h->difficulty;
     p.opponent_seeded = h->opponent_seeded ? 1 : 0;
     p.old_lists_off = h->old_lists_off;
+    p.act_stage_off = h->act_stage_off;
     p.cfg = h->dev_cfg;
 }
 
@@ -269,6 +270,25 @@ template <typename F> static cudaError_t for_each_step_kernel(const td_handle *h
     }
 }
 
+// reduced-precision observation variants (td_step_io.obs_format): Discrete actions, full writes, boards 10 / 20 / 30
+template <int CELLS, int NCHUNK, class OT, typename F> static cudaError_t for_each_kind_fmt(F f)
+{
+    cudaError_t e;
+    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK, 32, false, OT>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK, 32, false, OT>)) != cudaSuccess) return e;
+    return f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK, 32, false, OT>);
+}
+
+template <class OT, typename F> static cudaError_t for_each_fmt_kernel(const td_handle *h, F f)
+{
+    switch (h->L) {
+    case 10: return for_each_kind_fmt<100, 1, OT>(f);
+    case 20: return for_each_kind_fmt<400, 2, OT>(f);
+    case 30: return for_each_kind_fmt<900, 2, OT>(f);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
 template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes)
 {
     if (bytes <= 48 * 1024) return cudaSuccess;
@@ -305,6 +325,8 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     // slice = [record | scratch | pre-step tower / enemy cells (incremental observation) | twist staging area]
     h->old_lists_off = h->record_bytes + scratch;
     scratch += kOldListBytes;
+    h->act_stage_off = h->record_bytes + scratch;               // the attacker's action / RealAction (ATK, 2P)
+    if (env_kind != TD_KIND_DEF) scratch += TD_ROADS * TD_CLUSTER * 8;
     if (env_kind != TD_KIND_2P) scratch += kTwistStageBytes;
     h->smem_per_warp = h->record_bytes + scratch;
     h->obs_synced = nullptr;
@@ -323,6 +345,15 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     if (step_smem > 227 * 1024) { h->err = "map too large for shared memory"; return bail(TD_E_INVALID); }
     if ((e = for_each_step_kernel(h, false, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
         (e = for_each_step_kernel(h, true, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
+        ((h->L == 10 || h->L == 20 || h->L == 30) &&
+         ((e = for_each_fmt_kernel<__nv_bfloat16>(h, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
+          (e = for_each_fmt_kernel<uint8_t>(h, [&](auto kernel) { return allow_smem(kernel, step_smem); })) != cudaSuccess ||
+          (e = allow_smem(td_observe_kernel<100, __nv_bfloat16>, smem)) != cudaSuccess ||
+          (e = allow_smem(td_observe_kernel<400, __nv_bfloat16>, smem)) != cudaSuccess ||
+          (e = allow_smem(td_observe_kernel<900, __nv_bfloat16>, smem)) != cudaSuccess ||
+          (e = allow_smem(td_observe_kernel<100, uint8_t>, smem)) != cudaSuccess ||
+          (e = allow_smem(td_observe_kernel<400, uint8_t>, smem)) != cudaSuccess ||
+          (e = allow_smem(td_observe_kernel<900, uint8_t>, smem)) != cudaSuccess)) ||
         (e = allow_smem(td_reset_kernel, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel<0>, smem)) != cudaSuccess ||
         (e = allow_smem(td_observe_kernel<100>, smem)) != cudaSuccess ||
@@ -567,6 +598,13 @@ static int check_io(td_handle *h, const td_step_io *io)
         return fail(h, TD_E_INVALID, "td_step: opponent_dev / opponent_cluster_dev belong to the defender env");
     if (io->opponent_dev && io->opponent_cluster_dev)
         return fail(h, TD_E_INVALID, "td_step: give opponent_dev or opponent_cluster_dev, not both");
+    if (io->obs_format != TD_OBS_F32 && io->obs_dev) {
+        if (io->obs_format != TD_OBS_BF16 && io->obs_format != TD_OBS_U8) return fail(h, TD_E_INVALID, "td_step: unknown obs_format");
+        if (!(h->L == 10 || h->L == 20 || h->L == 30) || io->multi_action)
+            return fail(h, TD_E_INVALID, "td_step: reduced-precision observations need a 10 / 20 / 30 board and Discrete actions");
+        if (reinterpret_cast<uintptr_t>(io->obs_dev) & (io->obs_format == TD_OBS_BF16 ? 7 : 3))
+            return fail(h, TD_E_INVALID, "td_step: obs_dev is not aligned for this obs_format");
+    }
     return TD_OK;
 }
 
@@ -574,7 +612,7 @@ static int check_io(td_handle *h, const td_step_io *io)
 // td_step_io.obs_incremental is honoured only for the buffer the library itself filled last
 static bool obs_is_current(const td_handle *h, const td_step_io *io)
 {
-    return io->obs_incremental != 0 && io->obs_dev != nullptr && io->obs_dev == h->obs_synced;
+    return io->obs_incremental != 0 && io->obs_format == TD_OBS_F32 && io->obs_dev != nullptr && io->obs_dev == h->obs_synced;
 }
 
 // Where a step kernel goes: straight onto a stream, or into a graph under construction (td_step_host).
@@ -600,9 +638,10 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
         smem = (size_t)h->step_smem_kb * 1024;
         for_each_step_kernel(h, incremental, [&](auto kernel) { return allow_smem(kernel, smem); });
     }
-    const int want = step_variant(h->kind, io->multi_action != 0);
+    const bool reduced = io->obs_format != TD_OBS_F32 && io->obs_dev != nullptr;
+    const int want = reduced ? h->kind : step_variant(h->kind, io->multi_action != 0);
     int seen = 0;
-    cudaError_t le = for_each_step_kernel(h, incremental, [&](auto kernel) {
+    auto launch = [&](auto kernel) {
         if (seen++ != want) return cudaSuccess;
         if (!t.graph) {
             kernel<<<grid, block, smem, t.stream>>>(p);
@@ -617,7 +656,10 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
         kp.sharedMemBytes = (unsigned)smem;
         kp.kernelParams = args;
         return cudaGraphAddKernelNode(&t.node, t.graph, t.deps, t.n_deps, &kp);
-    });
+    };
+    cudaError_t le = !reduced ? for_each_step_kernel(h, incremental, launch)
+                     : io->obs_format == TD_OBS_BF16 ? for_each_fmt_kernel<__nv_bfloat16>(h, launch)
+                                                     : for_each_fmt_kernel<uint8_t>(h, launch);
     if (le != cudaSuccess) return fail(h, TD_E_CUDA, std::string("td_step: ") + cudaGetErrorString(le));
     return TD_OK;
 }
@@ -632,7 +674,7 @@ extern "C" int td_step(td_handle *h, const td_step_io *io, void *stream)
     t.stream = (cudaStream_t)stream;
     rc = launch_step(h, io, 0, h->n_envs, t, obs_is_current(h, io));
     if (rc != TD_OK) return rc;
-    h->obs_synced = io->obs_dev;
+    h->obs_synced = io->obs_format == TD_OBS_F32 ? io->obs_dev : nullptr;
     h->steps += h->n_envs;
     return TD_OK;
 }
@@ -659,6 +701,36 @@ extern "C" int td_observe(td_handle *h, float *obs_dev, void *stream)
     default: td_observe_kernel<0><<<grid, block, smem, s>>>(p, obs_dev); break;
     }
     h->obs_synced = obs_dev;
+    TD_CUDA(h, cudaGetLastError());
+    return TD_OK;
+}
+
+extern "C" int td_observe_as(td_handle *h, int obs_format, void *obs_dev, void *stream)
+{
+    if (!h) return TD_E_INVALID;
+    if (obs_format == TD_OBS_F32) return td_observe(h, static_cast<float *>(obs_dev), stream);
+    if (!obs_dev) return fail(h, TD_E_INVALID, "td_observe_as: obs_dev is NULL");
+    if (obs_format != TD_OBS_BF16 && obs_format != TD_OBS_U8) return fail(h, TD_E_INVALID, "td_observe_as: unknown obs_format");
+    if (!(h->L == 10 || h->L == 20 || h->L == 30)) return fail(h, TD_E_INVALID, "td_observe_as: board sizes 10 / 20 / 30 only");
+    if (reinterpret_cast<uintptr_t>(obs_dev) & (obs_format == TD_OBS_BF16 ? 7 : 3)) return fail(h, TD_E_INVALID, "td_observe_as: obs_dev is not aligned");
+    if (h->n_maps < 1) return fail(h, TD_E_STATE, "td_observe_as: upload maps and reset first");
+    TD_CUDA(h, cudaSetDevice(h->device));
+    StepParams p;
+    fill_params(h, p);
+    const int grid = grid_of(h), block = kWarpsPerCta * 32;
+    const size_t smem = smem_of(h);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (obs_format == TD_OBS_BF16) {
+        __nv_bfloat16 *o = static_cast<__nv_bfloat16 *>(obs_dev);
+        if (h->L == 10) td_observe_kernel<100, __nv_bfloat16><<<grid, block, smem, s>>>(p, o);
+        else if (h->L == 20) td_observe_kernel<400, __nv_bfloat16><<<grid, block, smem, s>>>(p, o);
+        else td_observe_kernel<900, __nv_bfloat16><<<grid, block, smem, s>>>(p, o);
+    } else {
+        uint8_t *o = static_cast<uint8_t *>(obs_dev);
+        if (h->L == 10) td_observe_kernel<100, uint8_t><<<grid, block, smem, s>>>(p, o);
+        else if (h->L == 20) td_observe_kernel<400, uint8_t><<<grid, block, smem, s>>>(p, o);
+        else td_observe_kernel<900, uint8_t><<<grid, block, smem, s>>>(p, o);
+    }
     TD_CUDA(h, cudaGetLastError());
     return TD_OK;
 }
@@ -734,7 +806,7 @@ static void host_chunk_copies(const td_handle *h, const td_step_io *io, const td
             segs[ns++] = Seg{static_cast<char *>(dst) + b * elem_bytes, static_cast<const char *>(src) + b * elem_bytes,
                              n * elem_bytes};
     };
-    add(host->obs_host, io->obs_dev, TD_NCHANNELS * cells * sizeof(float));
+    add(host->obs_host, io->obs_dev, TD_NCHANNELS * cells * (io->obs_format == TD_OBS_BF16 ? 2 : io->obs_format == TD_OBS_U8 ? 1 : 4));
     add(host->reward_host, io->reward_dev, sizeof(double));
     add(host->done_host, io->done_dev, 1);
     add(host->win_host, io->win_dev, 1);
@@ -908,7 +980,7 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
             begin += count;
         }
     }
-    h->obs_synced = io->obs_dev;
+    h->obs_synced = io->obs_format == TD_OBS_F32 ? io->obs_dev : nullptr;
     h->steps += h->n_envs;
     TD_CUDA(h, cudaStreamSynchronize(s));
     return TD_OK;

@@ -23,6 +23,7 @@
 // rewards are compared bit for bit.
 #pragma once
 #include "../../include/td_b200.h"
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -136,6 +137,7 @@ struct StepParams {
     int difficulty;
     int opponent_seeded;
     int old_lists_off;         // offset of the pre-step tower / enemy cell lists inside a slice
+    int act_stage_off;         // offset of the attacker's (3, 8) int64 action / RealAction inside a slice (ATK, 2P)
     td_step_io io;
     DevConfig cfg;             // per handle: travels with every launch in the kernel-parameter constant bank
 };
@@ -164,9 +166,8 @@ struct Ctx {
     int nt, ne, base_LP, steps, def_cd, atk_cd, fail, flags;
     // opponent generator cursor
     uint32_t *mt;
-    uint32_t win;
-    int mt_pos, win_k, win_n;
-    int ck, cn;                 // consumed / valid cached words
+    int mt_pos;
+    int ck, cn;                 // consumed / valid words of the (tempered) word cache
     bool static_dirty;          // the record's static map was replaced (reset)
 
     __device__ __forceinline__ int L() const { return CELLS ? kL : pp->L; }
@@ -192,6 +193,11 @@ struct Ctx {
     __device__ __forceinline__ uint32_t *old_lists() const
     {
         return reinterpret_cast<uint32_t *>(slice + pp->old_lists_off);
+    }
+    // the attacker's cluster action, later its RealAction: 24 int64 staged with the record (ATK / 2P envs)
+    __device__ __forceinline__ long long *act_stage() const
+    {
+        return reinterpret_cast<long long *>(slice + pp->act_stage_off);
     }
     // tail of the slice (envs with a scripted opponent only): staging area of the generator regeneration
     __device__ __forceinline__ uint32_t *twist_stage() const
@@ -262,7 +268,7 @@ __device__ __forceinline__ void ctx_bind(W &w, uint8_t *slice, const StepParams 
     w.gmask = W::G == 32 ? kFull : (0xffffu << w.gbase);
     w.ecap = TD_CAP_ENEMIES;
     w.mt = nullptr;
-    w.win = 0; w.mt_pos = 0; w.win_k = 0; w.win_n = 0;
+    w.mt_pos = 0;
     w.ck = 0; w.cn = 0;
     w.static_dirty = false;
 }
@@ -359,59 +365,59 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// One window of tempered words lives in the lanes (lane i holds the i-th next word) and is consumed with a
-// shuffle per draw.  It is refilled first from the words cached in the record (no memory round trip), then from
-// the generator state in HBM (twisting it when exhausted).  `ck` counts cached words moved into a window.
-// Out of line and by value: the draw sites (a dozen in the scripted defender) share one copy of the refill, and
-// the context stays in registers (a by-reference context would be forced to local memory).
-#ifndef TD_REFILL_NOINLINE
-#define TD_REFILL_NOINLINE 0      // measured on B200: out of line costs the attacker env 1.5 % (0.2715 -> 0.2754 ms)
-#endif
-#if TD_REFILL_NOINLINE
-#define TD_REFILL_ATTR __noinline__
-#else
-#define TD_REFILL_ATTR __forceinline__
-#endif
-struct MtRefill { uint32_t win; int ck, win_n, mt_pos; };
-__device__ TD_REFILL_ATTR MtRefill mt_refill(const uint32_t *cache, uint32_t *mt, uint32_t *stage, int lane, int G,
-                                           unsigned gmask, int ck, int cn, int mt_pos)
+// The generator words of a step are consumed from the record's word cache, tempered in place when the env is
+// loaded (temper_cache): a draw is one broadcast read from shared memory.  Only when a step needs more words than
+// the cache holds (the scripted defender's shuffle, a few percent of its steps) the out-of-line refill fetches the
+// next words from the generator state in HBM, twisting it when it is exhausted.
+struct MtRefill { int cn, mt_pos; };
+__device__ __noinline__ MtRefill mt_refill(uint32_t *cache, uint32_t *mt, uint32_t *stage, int lane, int G, unsigned gmask,
+                                           int mt_pos, int words)
 {
+    if (mt_pos >= kMtWords) { mt_twist_staged(mt, stage, lane, G, gmask); mt_pos = 0; }
+    const int n = min(words, kMtWords - mt_pos);
+    __syncwarp(gmask);                                  // every earlier read of the cache is done
+    for (int q = lane; q < n; q += G) cache[q] = mt_temper(mt[mt_pos + q]);
+    __syncwarp(gmask);
     MtRefill r;
-    uint32_t y = 0u;
-    if (ck < cn) {
-        const int n = min(G, cn - ck);
-        if (lane < n) y = cache[ck + lane];
-        ck += n;
-        r.win_n = n;
-    } else {
-        if (mt_pos >= kMtWords) { mt_twist_staged(mt, stage, lane, G, gmask); mt_pos = 0; }
-        const int n = min(G, kMtWords - mt_pos);
-        if (lane < n) y = mt[mt_pos + lane];
-        r.win_n = n;
-    }
-    r.win = mt_temper(y);
-    r.ck = ck;
+    r.cn = n;
     r.mt_pos = mt_pos;
     return r;
 }
 
 template <class W>
-__device__ __forceinline__ void mt_fill_window(W &w)
+__device__ __forceinline__ void mt_more_words(W &w)
 {
-    const MtRefill r = mt_refill(w.rng_cache(), w.mt, w.twist_stage(), w.lane, W::G, w.gmask, w.ck, w.cn, w.mt_pos);
-    w.win = r.win;
-    w.ck = r.ck;
-    w.win_n = r.win_n;
+    const MtRefill r = mt_refill(const_cast<uint32_t *>(w.rng_cache()), w.mt, w.twist_stage(), w.lane, W::G, w.gmask,
+                                 w.mt_pos, w.rng_words());
+    w.cn = r.cn;
     w.mt_pos = r.mt_pos;
-    w.win_k = 0;
+    w.ck = 0;
+}
+
+// raw cached words -> tempered, in place (the cache is rewritten with the next step's raw words before write-back)
+template <class W>
+__device__ __forceinline__ void temper_cache(W &w)
+{
+    uint32_t *cache = const_cast<uint32_t *>(w.rng_cache());
+    constexpr int kIters = W::kRngWords > 0 ? (W::kRngWords + W::G - 1) / W::G : 0;
+    if (kIters > 0) {
+#pragma unroll
+        for (int it = 0; it < kIters; ++it) {
+            const int q = w.lane + W::G * it;
+            if (q < w.cn) cache[q] = mt_temper(cache[q]);
+        }
+    } else {
+        for (int q = w.lane; q < w.cn; q += W::G) cache[q] = mt_temper(cache[q]);
+    }
+    gsync(w);
 }
 
 template <class W>
 __device__ __forceinline__ uint32_t mt_next(W &w)
 {
-    if (__builtin_expect(w.win_k == w.win_n, 0)) mt_fill_window(w);
-    const uint32_t r = gshfl(w, w.win, w.win_k);
-    ++w.win_k;
+    if (__builtin_expect(w.ck >= w.cn, 0)) mt_more_words(w);
+    const uint32_t r = w.rng_cache()[w.ck];
+    ++w.ck;
     ++w.mt_pos;
     return r;
 }
@@ -520,29 +526,20 @@ __device__ __forceinline__ int py_randbelow(W &w, int n)
 
 // random.shuffle(list) (for i in reversed(range(1, n)): j = randbelow(i + 1); swap) on a uint16 list in shared
 // memory.  The draws are serial by definition (rejections shift every later draw), so one lane runs the whole
-// loop alone over a buffer of tempered words the group fetched for it -- a fifth of the instructions of the
-// same loop with a group-wide draw per element.  `buf` holds kShufflePeek words.
-constexpr int kShufflePeek = 64;
+// loop alone, straight over the tempered word cache -- a fifth of the instructions of the same loop with a
+// group-wide draw per element.
 template <class W>
-__device__ __forceinline__ void py_shuffle_u16(W &w, uint16_t *list, int n, uint32_t *buf)
+__device__ __forceinline__ void py_shuffle_u16(W &w, uint16_t *list, int n)
 {
-    const int pos0 = w.hdr()->rng_pos;               // generator position the cached words start at
     int i = n - 1;
     while (i >= 1) {
-        if (w.mt_pos >= kMtWords) { mt_twist_staged(w.mt, w.twist_stage(), w.lane, W::G, w.gmask); w.mt_pos = 0; w.cn = 0; }
-        int avail = min(kShufflePeek, kMtWords - w.mt_pos);
-        const int cached = w.mt_pos >= pos0 ? w.cn - (w.mt_pos - pos0) : 0;
-        if (cached > 0) avail = min(avail, cached);             // stay inside the word cache while it lasts: no HBM trip
-        for (int q = w.lane; q < avail; q += W::G) {
-            const int a = w.mt_pos + q;
-            const uint32_t y = (a >= pos0 && a - pos0 < w.cn) ? w.rng_cache()[a - pos0] : w.mt[a];
-            buf[q] = mt_temper(y);
-        }
-        gsync(w);
-        int used = 0;
+        if (w.ck >= w.cn) mt_more_words(w);
+        int k = w.ck;
         if (w.lane == 0) {
-            while (i >= 1 && used < avail) {
-                const uint32_t r = buf[used++] >> __clz(i + 1);
+            const uint32_t *words = w.rng_cache();
+            const int end = w.cn;
+            while (i >= 1 && k < end) {
+                const uint32_t r = words[k++] >> __clz(i + 1);
                 if (r <= (uint32_t)i) {
                     const uint16_t t = list[i];
                     list[i] = list[r];
@@ -551,14 +548,12 @@ __device__ __forceinline__ void py_shuffle_u16(W &w, uint16_t *list, int n, uint
                 }
             }
         }
-        used = gshfl(w, used, 0);
+        k = gshfl(w, k, 0);
         i = gshfl(w, i, 0);
-        w.mt_pos += used;
+        w.mt_pos += k - w.ck;
+        w.ck = k;
         gsync(w);
     }
-    // the lane window is stale now; the word cache continues where the shuffle stopped
-    w.win_k = w.win_n = 0;
-    w.ck = w.mt_pos >= pos0 ? min(w.cn, w.mt_pos - pos0) : w.cn;     // behind pos0: twisted this step, cache is stale
 }
 
 template <class W>
@@ -938,11 +933,7 @@ __device__ __forceinline__ void opponent_tower(W &w, int difficulty, bool &dirty
             n += __popc(b);
         }
         gsync(w);
-        {
-            const int buf_off = (2 * n + 15) & ~15;
-            TD_CHECK(w, w.record_bytes() + buf_off + 4 * kShufflePeek <= w.pp->old_lists_off);
-            py_shuffle_u16(w, list, n, reinterpret_cast<uint32_t *>(w.scratch() + buf_off));
-        }
+        py_shuffle_u16(w, list, n);
         if (difficulty != 2) t = py_randbelow(w, TD_NTYPES);
         for (int k = 0; k < n; ++k) {
             int di = py_randbelow(w, 25);
@@ -1188,6 +1179,35 @@ __device__ __forceinline__ double board_step(W &w, int &kills_out, int &leaks_ou
 // (f) observation: dense planes with streaming float4 stores, then the sparse one-hots / enemy
 //     statistics as 4-byte stores on top (ordered after the dense pass by __syncwarp).
 
+// ------------------------------------------------------------------------------------------------
+// Observation element types (td_step_io.obs_format): float32 is the reference layout and the default; bfloat16 and
+// unorm8 are the opt-in reduced-precision planes of SURVEY.md 8(f) f4 -- same (45, L, L) layout, 2 / 1 bytes per
+// element.  bf16 = round-to-nearest-even of the float32 value; u8 = rint(min(v * 255, 255)) (values above 1 saturate).
+// Four consecutive elements ("quad") go out in one store: 16 / 8 / 4 bytes.
+template <class OT> struct ObsType;
+template <> struct ObsType<float> { static constexpr int kFormat = TD_OBS_F32; };
+template <> struct ObsType<__nv_bfloat16> { static constexpr int kFormat = TD_OBS_BF16; };
+template <> struct ObsType<uint8_t> { static constexpr int kFormat = TD_OBS_U8; };
+
+__device__ __forceinline__ uint32_t obs_u8(float v) { return __float2uint_rn(fminf(__fmul_rn(v, 255.f), 255.f)); }
+
+__device__ __forceinline__ void obs_store4(float *o, size_t quad, float4 v) { TD_ST(reinterpret_cast<float4 *>(o) + quad, v); }
+__device__ __forceinline__ void obs_store4(__nv_bfloat16 *o, size_t quad, float4 v)
+{
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const uint32_t *>(&lo);
+    u.y = *reinterpret_cast<const uint32_t *>(&hi);
+    reinterpret_cast<uint2 *>(o)[quad] = u;
+}
+__device__ __forceinline__ void obs_store4(uint8_t *o, size_t quad, float4 v)
+{
+    reinterpret_cast<uint32_t *>(o)[quad] = obs_u8(v.x) | (obs_u8(v.y) << 8) | (obs_u8(v.z) << 16) | (obs_u8(v.w) << 24);
+}
+__device__ __forceinline__ void obs_store1(float *o, size_t i, float v) { o[i] = v; }
+__device__ __forceinline__ void obs_store1(__nv_bfloat16 *o, size_t i, float v) { o[i] = __float2bfloat16_rn(v); }
+__device__ __forceinline__ void obs_store1(uint8_t *o, size_t i, float v) { o[i] = (uint8_t)obs_u8(v); }
+
 __device__ __forceinline__ void fill_planes(float *o, int first_plane, int n_planes, int cells, float v, int lane, int stride)
 {
     float4 *p = reinterpret_cast<float4 *>(o + (size_t)first_plane * cells);
@@ -1203,15 +1223,15 @@ __device__ __forceinline__ void fill_planes_scalar(float *o, int first_plane, in
 }
 
 // N4 consecutive float4 of one value, fully unrolled: one STG.128 with an immediate offset per 512 bytes.
-template <int N4, int G>
-__device__ __forceinline__ void store_run(float4 *p, float v, int lane)
+template <int N4, int G, class OT>
+__device__ __forceinline__ void store_run(OT *o, int first_quad, float v, int lane)
 {
     const float4 x = make_float4(v, v, v, v);
     constexpr int kFullIters = N4 / G, kRem = N4 % G;
-    p += lane;
+    const size_t q0 = (size_t)first_quad + lane;
 #pragma unroll
-    for (int k = 0; k < kFullIters; ++k) TD_ST(p + G * k, x);
-    if (kRem != 0 && lane < kRem) TD_ST(p + G * kFullIters, x);
+    for (int k = 0; k < kFullIters; ++k) obs_store4(o, q0 + G * k, x);
+    if (kRem != 0 && lane < kRem) obs_store4(o, q0 + G * kFullIters, x);
 }
 
 // CELLS > 0: compile-time board size (runs of equal planes are unrolled stores with immediate offsets).
@@ -1269,18 +1289,19 @@ struct SmallDiv {
     }
 };
 
-template <int NT, class W>
-__device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
+template <int NT, class W, class OT>
+__device__ __forceinline__ void obs_dense(const W &w, OT *o, int tid)
 {
     constexpr int CELLS = W::kCells;
+    constexpr bool kF32 = ObsType<OT>::kFormat == TD_OBS_F32;
+    static_assert(kF32 || CELLS > 0, "reduced-precision observations exist for the specialised board sizes");
     const int cells = CELLS > 0 ? CELLS : w.ncells();
-    const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+    const bool vec = (cells & 3) == 0 && ((reinterpret_cast<uintptr_t>(o) & (4 * sizeof(OT) - 1)) == 0);
     const SmallDiv by_maxd((float)w.mh()->maxd_p1);
     const float *pv = reinterpret_cast<const float *>(w.scratch()) + 64;
-    if (CELLS > 0 && vec) {
+    if (CELLS > 0 && (vec || !kF32)) {
         constexpr int C4 = CELLS > 0 ? CELLS / 4 : 1;
         constexpr int kIters = (C4 + NT - 1) / NT;
-        float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
         const uchar4 *db = reinterpret_cast<const uchar4 *>(w.dist());
         const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
@@ -1291,27 +1312,28 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
                 const uchar4 c = cb[q], d = db[q], m = mb[q];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    TD_ST(o4 + k * C4 + q, make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
-                                                        (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
-                TD_ST(o4 + 9 * C4 + q, make_float4(by_maxd((float)d.x), by_maxd((float)d.y),
-                                                    by_maxd((float)d.z), by_maxd((float)d.w)));
-                TD_ST(o4 + 14 * C4 + q, make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
-                                                     m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
+                    obs_store4(o, (size_t)(k * C4 + q), make_float4((float)((c.x >> k) & 1), (float)((c.y >> k) & 1),
+                                                                     (float)((c.z >> k) & 1), (float)((c.w >> k) & 1)));
+                obs_store4(o, (size_t)(9 * C4 + q), make_float4(by_maxd((float)d.x), by_maxd((float)d.y),
+                                                                 by_maxd((float)d.z), by_maxd((float)d.w)));
+                obs_store4(o, (size_t)(14 * C4 + q), make_float4(m.x == 0 ? 1.f : 0.f, m.y == 0 ? 1.f : 0.f,
+                                                                  m.z == 0 ? 1.f : 0.f, m.w == 0 ? 1.f : 0.f));
             }
         }
-        store_run<C4, NT>(o4 + 4 * C4, 0.f, tid);
-        store_run<C4, NT>(o4 + 5 * C4, pv[5], tid);
-        store_run<3 * C4, NT>(o4 + 6 * C4, 0.f, tid);
-        store_run<C4, NT>(o4 + 10 * C4, 0.f, tid);
+        store_run<C4, NT>(o, 4 * C4, 0.f, tid);
+        store_run<C4, NT>(o, 5 * C4, pv[5], tid);
+        store_run<3 * C4, NT>(o, 6 * C4, 0.f, tid);
+        store_run<C4, NT>(o, 10 * C4, 0.f, tid);
 #pragma unroll
-        for (int k = 11; k < 14; ++k) store_run<C4, NT>(o4 + k * C4, pv[k], tid);
-        store_run<6 * C4, NT>(o4 + 15 * C4, 0.f, tid);
+        for (int k = 11; k < 14; ++k) store_run<C4, NT>(o, k * C4, pv[k], tid);
+        store_run<6 * C4, NT>(o, 15 * C4, 0.f, tid);
 #pragma unroll
-        for (int k = 21; k < 25; ++k) store_run<C4, NT>(o4 + k * C4, pv[k], tid);
-        store_run<16 * C4, NT>(o4 + 25 * C4, 0.f, tid);
+        for (int k = 21; k < 25; ++k) store_run<C4, NT>(o, k * C4, pv[k], tid);
+        store_run<16 * C4, NT>(o, 25 * C4, 0.f, tid);
 #pragma unroll
-        for (int k = 41; k < 45; ++k) store_run<C4, NT>(o4 + k * C4, pv[k], tid);
-    } else if (vec) {
+        for (int k = 41; k < 45; ++k) store_run<C4, NT>(o, k * C4, pv[k], tid);
+    } else if constexpr (kF32) {
+      if (vec) {
         const int c4 = cells >> 2;
         float4 *o4 = reinterpret_cast<float4 *>(o);
         const uchar4 *cb = reinterpret_cast<const uchar4 *>(w.cells());
@@ -1343,7 +1365,7 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
         for (int k = 21; k < 25; ++k) fill_planes(o, k, 1, cells, pv[k], tid, NT);
         fill_planes(o, 25, 16, cells, 0.f, tid, NT);
         for (int k = 41; k < 45; ++k) fill_planes(o, k, 1, cells, pv[k], tid, NT);
-    } else {
+      } else {
         for (int q = tid; q < cells; q += NT) {
             uint8_t c = w.cells()[q];
 #pragma unroll
@@ -1353,13 +1375,14 @@ __device__ __forceinline__ void obs_dense(const W &w, float *o, int tid)
         }
         for (int k = 4; k < TD_NCHANNELS; ++k)
             if (k != 9 && k != 14) fill_planes_scalar(o, k, 1, cells, pv[k], tid, NT);
+      }
     }
 }
 
 // Step 3: the sparse one-hots and enemy statistics, 4-byte stores on top of the dense planes (the caller
 // orders them after every dense store to this env: __syncwarp for one group, __syncthreads for a CTA sweep).
-template <class W>
-__device__ __forceinline__ void obs_sparse(W &w, float *o)
+template <class W, class OT>
+__device__ __forceinline__ void obs_sparse(W &w, OT *o)
 {
     const DevConfig &cc = w.pp->cfg;
     constexpr int CELLS = W::kCells;
@@ -1381,15 +1404,12 @@ __device__ __forceinline__ void obs_sparse(W &w, float *o)
         }
     }
     gsync(w);   // also orders the dense stores above before the sparse stores below
-#ifdef TD_EXP_NO_SPARSE
-    return;
-#endif
-    if (lane == 0) o[(size_t)4 * cells + w.mh()->end] = 1.f;
-    if (lane < w.mh()->num_roads) o[(size_t)(6 + lane) * cells + w.mh()->start[lane]] = 1.f;
+    if (lane == 0) obs_store1(o, (size_t)4 * cells + w.mh()->end, 1.f);
+    if (lane < w.mh()->num_roads) obs_store1(o, (size_t)(6 + lane) * cells + w.mh()->start[lane], 1.f);
     for (int t = lane; t < w.nt; t += W::G) {
         const td_tower_rec &T = w.tw()[t];
-        o[(size_t)(15 + (T.type_lv >> 2)) * cells + T.loc] = 1.f;
-        o[(size_t)(17 + (T.type_lv & 3)) * cells + T.loc] = 1.f;
+        obs_store1(o, (size_t)(15 + (T.type_lv >> 2)) * cells + T.loc, 1.f);
+        obs_store1(o, (size_t)(17 + (T.type_lv & 3)) * cells + T.loc, 1.f);
     }
     if (one_pass) {
         // lanes of one (cell, type) group find each other with one match instruction; every lane then folds its
@@ -1412,10 +1432,10 @@ __device__ __forceinline__ void obs_sparse(W &w, float *o)
         }
         if (have && lane == __ffs(group) - 1) {
             const float cnt = (float)__popc(group);
-            o[(size_t)(25 + ty) * cells + loc] = mn;
-            o[(size_t)(29 + ty) * cells + loc] = mx;
-            o[(size_t)(33 + ty) * cells + loc] = __fdiv_rn(sum, cnt);
-            o[(size_t)(37 + ty) * cells + loc] = cnt * 0.125f;
+            obs_store1(o, (size_t)(25 + ty) * cells + loc, mn);
+            obs_store1(o, (size_t)(29 + ty) * cells + loc, mx);
+            obs_store1(o, (size_t)(33 + ty) * cells + loc, __fdiv_rn(sum, cnt));
+            obs_store1(o, (size_t)(37 + ty) * cells + loc, cnt * 0.125f);
         }
         return;
     }
@@ -1435,10 +1455,10 @@ __device__ __forceinline__ void obs_sparse(W &w, float *o)
             }
         }
         if (leader) {
-            o[(size_t)(25 + ty) * cells + loc] = mn;
-            o[(size_t)(29 + ty) * cells + loc] = mx;
-            o[(size_t)(33 + ty) * cells + loc] = __fdiv_rn(sum, cnt);
-            o[(size_t)(37 + ty) * cells + loc] = cnt * 0.125f;
+            obs_store1(o, (size_t)(25 + ty) * cells + loc, mn);
+            obs_store1(o, (size_t)(29 + ty) * cells + loc, mx);
+            obs_store1(o, (size_t)(33 + ty) * cells + loc, __fdiv_rn(sum, cnt));
+            obs_store1(o, (size_t)(37 + ty) * cells + loc, cnt * 0.125f);
         }
     }
 }
@@ -1458,9 +1478,9 @@ __device__ __forceinline__ void obs_dense_incremental(W &w, float *o)
     const float *pv = reinterpret_cast<const float *>(w.scratch()) + 64;
     float4 *o4 = reinterpret_cast<float4 *>(o);
     const uchar4 *mb = reinterpret_cast<const uchar4 *>(w.map6());
-    store_run<C4, W::G>(o4 + 5 * C4, pv[5], lane);
+    store_run<C4, W::G>(o, 5 * C4, pv[5], lane);
 #pragma unroll
-    for (int k = 11; k < 14; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
+    for (int k = 11; k < 14; ++k) store_run<C4, W::G>(o, k * C4, pv[k], lane);
     constexpr int kIters = (C4 + W::G - 1) / W::G;
 #pragma unroll
     for (int it = 0; it < kIters; ++it) {
@@ -1472,9 +1492,9 @@ __device__ __forceinline__ void obs_dense_incremental(W &w, float *o)
         }
     }
 #pragma unroll
-    for (int k = 21; k < 25; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
+    for (int k = 21; k < 25; ++k) store_run<C4, W::G>(o, k * C4, pv[k], lane);
 #pragma unroll
-    for (int k = 41; k < 45; ++k) store_run<C4, W::G>(o4 + k * C4, pv[k], lane);
+    for (int k = 41; k < 45; ++k) store_run<C4, W::G>(o, k * C4, pv[k], lane);
     const uint32_t *old = w.old_lists();
     const int nt0 = (int)old[0], ne0 = (int)old[1];
     for (int t = lane; t < nt0; t += W::G) {
@@ -1492,8 +1512,8 @@ __device__ __forceinline__ void obs_dense_incremental(W &w, float *o)
     // obs_sparse starts with the group barrier that orders these clears before the new entries
 }
 
-template <class W>
-__device__ __forceinline__ void write_obs(W &w, float *o)
+template <class W, class OT>
+__device__ __forceinline__ void write_obs(W &w, OT *o)
 {
     obs_prepare(w);
     obs_dense<W::G>(w, o, w.lane);
@@ -1528,22 +1548,28 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
     // the record and the inputs are requested together: one round trip
     issue_env_load(w, rec);
     long long in_def = 0;
-    long long atk_mine[TD_ROADS] = {TD_NTYPES, TD_NTYPES, TD_NTYPES};      // lanes 0..7 hold road i's cluster slots
     int in_opp = 0xff;
     if (KIND != TD_KIND_ATK && !MULTI) in_def = io.def_action_dev[env];
     if (KIND == TD_KIND_ATK && io.def_action_dev != nullptr) in_def = io.def_action_dev[env];     // host-resolved build
     unsigned in_cluster = 0xffffffffu;
     if (KIND == TD_KIND_DEF && io.opponent_cluster_dev != nullptr) in_cluster = io.opponent_cluster_dev[env];
-    if (KIND != TD_KIND_DEF && lane < TD_CLUSTER) {
-#pragma unroll
-        for (int i = 0; i < TD_ROADS; ++i)
-            atk_mine[i] = io.atk_action_dev[(size_t)env * TD_ROADS * TD_CLUSTER + i * TD_CLUSTER + lane];
+    if (KIND != TD_KIND_DEF) {
+        // the attacker's (3, 8) int64 action travels with the record: 12 asynchronous 16-byte copies into the slice,
+        // where summon_cluster turns it into the RealAction in place (no registers held across the step)
+        const long long *src = reinterpret_cast<const long long *>(io.atk_action_dev) + (size_t)env * TD_ROADS * TD_CLUSTER;
+        if ((reinterpret_cast<uintptr_t>(io.atk_action_dev) & 15) == 0) {
+            async_copy16(w.act_stage(), src, TD_ROADS * TD_CLUSTER / 2, lane, GW);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+            for (int q = lane; q < TD_ROADS * TD_CLUSTER; q += GW) w.act_stage()[q] = src[q];
+        }
     }
     if (KIND == TD_KIND_DEF && io.opponent_dev != nullptr) in_opp = io.opponent_dev[env];
     w.ecap = GW * NCHUNK;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     gsync(w);
     finish_env_load(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
+    if (device_opponent) temper_cache(w);
     if (INC) {
         // remember where towers and enemies stand in the observation the caller's buffer still holds
         uint32_t *old = w.old_lists();
@@ -1576,7 +1602,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
             // one instance of the cluster code for all roads (kept rolled: the kernel is instruction-cache bound)
 #pragma unroll 1
             for (int i = 0; i < nr; ++i) {
-                long long cur = i == 0 ? atk_mine[0] : (i == 1 ? atk_mine[1] : atk_mine[2]);
+                long long cur = lane < TD_CLUSTER ? w.act_stage()[i * TD_CLUSTER + lane] : (long long)TD_NTYPES;
                 int code = 0;
                 bool skip = false;
                 if (!(KIND == TD_KIND_2P && MULTI))
@@ -1587,7 +1613,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
                     if (KIND == TD_KIND_2P) { cur = before; w.atk_cd = cc.atk_interval; }   // tuple truthiness
                     else if (res) w.atk_cd = cc.atk_interval;
                     code = w.fail;
-                    if (i == 0) atk_mine[0] = cur; else if (i == 1) atk_mine[1] = cur; else atk_mine[2] = cur;
+                    if (lane < TD_CLUSTER) w.act_stage()[i * TD_CLUSTER + lane] = cur;          // RealAction
                 }
                 if (n_fail_atk == 0) fail_atk[0] = code; else if (n_fail_atk == 1) fail_atk[1] = code; else fail_atk[2] = code;
                 ++n_fail_atk;
@@ -1680,10 +1706,9 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
         }
         if (w.flags) p.stats[env].flags |= (uint32_t)w.flags;
     }
-    if (KIND != TD_KIND_DEF && io.real_atk_dev && lane < TD_CLUSTER) {
-#pragma unroll
-        for (int i = 0; i < TD_ROADS; ++i)
-            io.real_atk_dev[(size_t)env * TD_ROADS * TD_CLUSTER + i * TD_CLUSTER + lane] = atk_mine[i];
+    if (KIND != TD_KIND_DEF && io.real_atk_dev) {
+        for (int q = lane; q < TD_ROADS * TD_CLUSTER; q += GW)
+            io.real_atk_dev[(size_t)env * TD_ROADS * TD_CLUSTER + q] = w.act_stage()[q];
     }
     if (io.packed_out_dev != nullptr) {
         // every small output of the env in one record and one coalesced store (the buffer may be host memory)
@@ -1699,15 +1724,8 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
         if (lane == 1) v = make_int4((MULTI || KIND == TD_KIND_ATK) ? 0 : fail_def, (int)fl, 0, 0);
         if (KIND != TD_KIND_DEF) {
             if (lane == 2) v = make_int4(n_fail_atk, fail_atk[0], fail_atk[1], fail_atk[2]);
-            // lanes 4..15 carry real_atk[2q], real_atk[2q + 1] (q = lane - 4): slots k0, k0 + 1 of road q / 4
-            const int q = (lane - 4) & 15, k0 = (q & 3) * 2, road = q >> 2;
-            long long a0 = 0, a1 = 0;
-#pragma unroll
-            for (int i = 0; i < TD_ROADS; ++i) {
-                const long long x0 = gshfl(w, atk_mine[i], k0), x1 = gshfl(w, atk_mine[i], k0 + 1);
-                if (road == i) { a0 = x0; a1 = x1; }
-            }
-            if (lane >= 4 && lane < 16) v = make_int4((int)a0, (int)(a0 >> 32), (int)a1, (int)(a1 >> 32));
+            // lanes 4..15 carry real_atk[2q], real_atk[2q + 1] (q = lane - 4), straight from the slice
+            if (lane >= 4 && lane < 16) v = reinterpret_cast<const int4 *>(w.act_stage())[lane - 4];
         }
         if (lane < kStride / 16) po[lane] = v;
     }
@@ -1725,7 +1743,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
 
 // INC: the observation is an in-place update of the previous one (td_step_io.obs_incremental, vouched for by the
 // engine); a separate instantiation, so that the full-write kernels carry none of its code.
-template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC>
+template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC, class OT = float>
 __global__ void __launch_bounds__(kWarpsPerCta * 32, KIND == TD_KIND_ATK ? TD_MIN_BLOCKS_ATK : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
@@ -1749,7 +1767,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, KIND == TD_KIND_ATK ? TD_MI
         store_env<true>(w, p, rec, dirty, false);
     }
     if (p.io.obs_dev) {
-        float *o = p.io.obs_dev + (size_t)env * TD_NCHANNELS * w.ncells();
+        OT *o = reinterpret_cast<OT *>(p.io.obs_dev) + (size_t)env * TD_NCHANNELS * w.ncells();
         if constexpr (INC && CELLS > 0) {
             obs_prepare(w);
             if (!w.static_dirty && (reinterpret_cast<uintptr_t>(o) & 15) == 0) obs_dense_incremental(w, o);
@@ -1787,8 +1805,8 @@ td_reset_kernel(const __grid_constant__ StepParams p, const uint8_t *mask, const
     store_env(w, p, rec, true);
 }
 
-template <int CELLS>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const __grid_constant__ StepParams p, float *obs)
+template <int CELLS, class OT = float>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) td_observe_kernel(const __grid_constant__ StepParams p, OT *obs)
 {
     const int warp = threadIdx.x >> 5;
     const int env = blockIdx.x * kWarpsPerCta + warp;

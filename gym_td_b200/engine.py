@@ -17,6 +17,7 @@ NT, NLV, CLUSTER, ROADS, NCH, MAX_L = 4, 2, 8, 3, 45, 64
 CAP_TOWERS, CAP_ENEMIES = 32, 64
 KIND_DEF, KIND_ATK, KIND_2P = 0, 1, 2
 KINDS = {"def": KIND_DEF, "atk": KIND_ATK, "2p": KIND_2P}
+OBS_FORMATS = {"f32": 0, "bf16": 1, "u8": 2}
 OPTIONS = {"host_chunks": 1, "host_graph": 2, "step_smem_kb": 3, "obs_smem_kb": 4}
 
 _TABLES_F64 = ["enemy_LP", "enemy_speed", "enemy_defense", "enemy_cost", "tower_attack", "tower_cost",
@@ -48,7 +49,7 @@ class TdStepIO(C.Structure):
                 ("obs_dev", C.c_void_p), ("reward_dev", C.c_void_p), ("done_dev", C.c_void_p),
                 ("win_dev", C.c_void_p), ("allow_next_dev", C.c_void_p), ("real_def_dev", C.c_void_p),
                 ("real_atk_dev", C.c_void_p), ("fail_def_dev", C.c_void_p), ("fail_atk_dev", C.c_void_p),
-                ("obs_incremental", C.c_int32), ("reserved_", C.c_int32), ("opponent_cluster_dev", C.c_void_p),
+                ("obs_incremental", C.c_int32), ("obs_format", C.c_int32), ("opponent_cluster_dev", C.c_void_p),
                 ("packed_out_dev", C.c_void_p)]
 
 
@@ -94,7 +95,7 @@ EXPORTS = ["td_abi_version", "td_last_error", "td_default_config", "td_mapgen", 
            "td_destroy", "td_set_config", "td_get_layout", "td_upload_maps", "td_set_map_stride", "td_reset",
            "td_seed_opponent", "td_set_difficulty", "td_step", "td_observe", "td_step_host", "td_get_state",
            "td_set_state", "td_get_opponent", "td_get_stats", "td_reset_stats", "td_rollout_mask", "td_rollout_record",
-           "td_gae", "td_snapshot", "td_observe_snapshot", "td_set_option", "td_packed_stride", "td_invalidate_obs"]
+           "td_gae", "td_snapshot", "td_observe_snapshot", "td_set_option", "td_packed_stride", "td_invalidate_obs", "td_observe_as"]
 
 
 def lib():
@@ -138,6 +139,7 @@ def lib():
                              C.c_void_p, C.c_void_p, C.c_void_p]
         L.td_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.td_invalidate_obs.argtypes = [C.c_void_p]
+        L.td_observe_as.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         if L.td_abi_version() != 3:
             raise ImportError("libtd_b200.so ABI version mismatch")
         _lib = L
@@ -278,8 +280,9 @@ class Engine(object):
     @staticmethod
     def make_io(def_action=None, atk_action=None, opponent=None, multi_action=False, auto_reset=False, obs=None,
                 reward=None, done=None, win=None, allow_next=None, real_def=None, real_atk=None, fail_def=None,
-                fail_atk=None, obs_incremental=False, opponent_cluster=None, packed_out=None):
+                fail_atk=None, obs_incremental=False, opponent_cluster=None, packed_out=None, obs_format="f32"):
         io = TdStepIO()
+        io.obs_format = OBS_FORMATS[obs_format] if isinstance(obs_format, str) else int(obs_format)
         io.packed_out_dev = _ptr(packed_out)
         io.opponent_cluster_dev = _ptr(opponent_cluster)
         io.obs_incremental = int(bool(obs_incremental))
@@ -299,8 +302,9 @@ class Engine(object):
     def invalidate_obs(self):
         self._check(self._lib.td_invalidate_obs(self._h))
 
-    def observe(self, obs, stream=0):
-        self._check(self._lib.td_observe(self._h, _ptr(obs), stream))
+    def observe(self, obs, stream=0, obs_format="f32"):
+        fmt = OBS_FORMATS[obs_format] if isinstance(obs_format, str) else int(obs_format)
+        self._check(self._lib.td_observe_as(self._h, fmt, _ptr(obs), stream))
 
     # -- state / statistics ---------------------------------------------------------------------
     def get_state_raw(self, first_env=0, n=None):

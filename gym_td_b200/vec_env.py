@@ -57,7 +57,7 @@ class _Info(dict):
 class TDVecEnv(object):
     def __init__(self, kind, map_size, num_envs, seed=0, device=0, difficulty=1, auto_reset=True, env_offset=0,
                  n_maps=None, scripted_opponent=True, multi_action=None, cfg=None, mapgen_threads=None,
-                 incremental_obs=False):
+                 incremental_obs=False, obs_format="f32"):
         if kind not in E.KINDS:
             raise ValueError("kind must be one of %r" % (sorted(E.KINDS),))
         self.kind, self.map_size, self.num_envs = kind, int(map_size), int(num_envs)
@@ -84,7 +84,15 @@ class TDVecEnv(object):
             self.engine.set_difficulty(difficulty)
             self.engine.seed_opponent_python((np.arange(num_envs, dtype=np.uint64) + base).astype(np.uint32))
         N, L, dev = self.num_envs, self.map_size, self.device
-        self._obs = torch.empty((N, E.NCH, L, L), dtype=torch.float32, device=dev)
+        # obs_format: "f32" is the reference's tensor; "bf16" / "u8" are the opt-in reduced-precision planes (SURVEY 8(f)
+        # f4): same (N, 45, L, L) layout, the float32 value rounded to bfloat16 / quantised to rint(min(255 v, 255))
+        if obs_format not in E.OBS_FORMATS:
+            raise ValueError("obs_format must be one of %r" % (sorted(E.OBS_FORMATS),))
+        if obs_format != "f32" and (self.multi_action or L not in (10, 20, 30) or incremental_obs):
+            raise ValueError("reduced-precision observations: boards 10 / 20 / 30, Discrete actions, full writes")
+        self.obs_format = obs_format
+        self._obs_dtype = {"f32": torch.float32, "bf16": torch.bfloat16, "u8": torch.uint8}[obs_format]
+        self._obs = torch.empty((N, E.NCH, L, L), dtype=self._obs_dtype, device=dev)
         # the small per-step outputs live in one slab (mirrored by one pinned host slab in step_host, so that
         # td_step_host moves them with a single device->host copy)
         self._layout, off = {}, 0
@@ -120,8 +128,8 @@ class TDVecEnv(object):
     @obs.setter
     def obs(self, t):
         N, L = self.num_envs, self.map_size
-        if tuple(t.shape) != (N, E.NCH, L, L) or t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
-            raise ValueError("obs must be a contiguous CUDA float32 tensor of shape %r" % ((N, E.NCH, L, L),))
+        if tuple(t.shape) != (N, E.NCH, L, L) or t.dtype != self._obs_dtype or not t.is_cuda or not t.is_contiguous():
+            raise ValueError("obs must be a contiguous CUDA %s tensor of shape %r" % (self._obs_dtype, (N, E.NCH, L, L)))
         self._obs = t
         self.engine.invalidate_obs()
 
@@ -149,7 +157,11 @@ class TDVecEnv(object):
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
         if map_ids is not None:
             map_ids = map_ids.to(device=self.device, dtype=torch.int32).contiguous()
-        self.engine.reset(mask=mask, map_ids=map_ids, obs=self.obs, stream=s)
+        if self.obs_format == "f32":
+            self.engine.reset(mask=mask, map_ids=map_ids, obs=self.obs, stream=s)
+        else:                                   # td_reset writes float32: restart, then one observation pass
+            self.engine.reset(mask=mask, map_ids=map_ids, obs=None, stream=s)
+            self.engine.observe(self.obs, s, self.obs_format)
         return self.obs
 
     def _split(self, action):
@@ -169,6 +181,7 @@ class TDVecEnv(object):
                 real_atk=self.real_atk, fail_def=self.fail_def, fail_atk=self.fail_atk)
         io.auto_reset = int(self.auto_reset)
         io.obs_incremental = int(self.incremental_obs)
+        io.obs_format = E.OBS_FORMATS[self.obs_format]
         io.obs_dev = E._ptr(self.obs)
         io.def_action_dev = d.data_ptr() if d is not None else None
         io.atk_action_dev = a.data_ptr() if a is not None else None
@@ -231,7 +244,7 @@ class TDVecEnv(object):
         h = self._host_buffers()
         d, a = self._split(action)
         if want_obs and h["obs"] is None:
-            h["obs"] = torch.empty(self.obs.shape, dtype=torch.float32).pin_memory()
+            h["obs"] = torch.empty(self.obs.shape, dtype=self._obs_dtype).pin_memory()
         io = self._io(h["def_dev"] if d is not None else None, h["atk_dev"] if a is not None else None)
         hio = self._hio_cache
         if hio is None:
@@ -256,7 +269,7 @@ class TDVecEnv(object):
         if self.kind != "atk" and self.multi_action:
             d2h += self.real_def.numel() * 8
         if want_obs:
-            d2h += N * E.NCH * L * L * 4
+            d2h += N * E.NCH * L * L * self.obs.element_size()
         return h2d, d2h
 
     # -- statistics -------------------------------------------------------------------------------
@@ -321,7 +334,7 @@ class TDVecEnv(object):
             # the cached words are re-read from the restored generator state on the first draw
             self.engine.seed_opponent(d["opponent"].numpy().astype(np.uint32))
         self._allow.copy_(d["allow"].to(self.device))
-        self.engine.observe(self.obs, torch.cuda.current_stream(self.device).cuda_stream)
+        self.engine.observe(self.obs, torch.cuda.current_stream(self.device).cuda_stream, self.obs_format)
         return self.obs
 
     def close(self):

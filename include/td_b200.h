@@ -45,6 +45,9 @@ extern "C" {
 enum { TD_OK = 0, TD_E_INVALID = -1, TD_E_CUDA = -2, TD_E_ALLOC = -3, TD_E_STATE = -4,
        TD_E_OVERFLOW = -5 };
 
+/* observation element types (td_step_io.obs_format, td_observe_as) */
+enum { TD_OBS_F32 = 0, TD_OBS_BF16 = 1, TD_OBS_U8 = 2 };
+
 /* env kinds (TDDefense / TDAttack / TDMulti) */
 enum { TD_KIND_DEF = 0, TD_KIND_ATK = 1, TD_KIND_2P = 2 };
 
@@ -136,7 +139,12 @@ typedef struct td_step_io {
                                         library cannot vouch for the buffer: another pointer than last time, after
                                         td_set_state, for envs that were reset inside the step, for board sizes
                                         without a specialised kernel. */
-    int32_t reserved_;
+    int32_t obs_format;              /* TD_OBS_F32 (0, default): obs_dev is float32, the reference layout.  TD_OBS_BF16 /
+                                        TD_OBS_U8 (ABI 3): obs_dev points to [n,45,L,L] bfloat16 / uint8 elements instead
+                                        (reduced-precision planes): bf16 = the float32 value rounded to
+                                        nearest-even, u8 = rint(min(v * 255, 255)).  Board sizes 10 / 20 / 30, Discrete
+                                        defender actions, full writes only (obs_incremental is ignored); obs_dev must
+                                        be 8- / 4-byte aligned. */
     /* more inputs (ABI 3) */
     const uint32_t *opponent_cluster_dev; /* DEF only, optional host-resolved scripted attacker with a free cluster
                                         (random_enemy_lv0 on the env's np_random, TDGymBasic.py:87-89): [n] words,
@@ -270,6 +278,8 @@ int td_step(td_handle *h, const td_step_io *io, void *stream);
 int td_invalidate_obs(td_handle *h);
 /* observation of the current state only (kernel (f) alone) */
 int td_observe(td_handle *h, float *obs_dev, void *stream);
+/* the same in a reduced-precision element type (TD_OBS_BF16 / TD_OBS_U8; TD_OBS_F32 = td_observe) */
+int td_observe_as(td_handle *h, int obs_format, void *obs_dev, void *stream);
 
 /* Host-buffer variant (the gym-facing call): copies the actions host->device, steps, copies
  * the small outputs (and the observation if obs_host != NULL) device->host, and synchronises.

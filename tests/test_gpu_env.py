@@ -312,6 +312,44 @@ def test_rebinding_obs_restarts_the_incremental_update():
     a.close(), b.close()
 
 
+@pytest.mark.parametrize("kind,L", [("def", 10), ("atk", 10), ("2p", 20), ("def", 30)])
+def test_reduced_precision_observation_planes(kind, L):
+    """the opt-in bfloat16 / uint8 observation tensors are exactly the float32 observation rounded
+    (bf16: nearest-even) resp. quantised (u8: rint(min(255 v, 255))), every step, through resets and td_observe."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    N = 96
+    envs = {f: TDVecEnv(kind, L, N, seed=8, auto_reset=True, obs_format=f) for f in ("f32", "bf16", "u8")}
+    for e in envs.values():
+        e.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+
+    def check(tag):
+        ref = envs["f32"].obs
+        assert torch.equal(envs["bf16"].obs.view(torch.int16), ref.to(torch.bfloat16).view(torch.int16)), tag
+        want = torch.clamp(torch.round(ref * 255.0), 0, 255).to(torch.uint8)
+        assert torch.equal(envs["u8"].obs, want), tag
+        assert envs["bf16"].obs.dtype == torch.bfloat16 and envs["u8"].obs.element_size() == 1
+
+    check("reset")
+    for t in range(150):
+        d = torch.randint(0, 6 * L * L + 1, (N,), dtype=torch.int64, device="cuda", generator=g)
+        a = torch.randint(0, 5, (N, 3, 8), dtype=torch.int64, device="cuda", generator=g)
+        act = d if kind == "def" else a if kind == "atk" else {"Attacker": a, "Defender": d}
+        outs = {f: e.step(act) for f, e in envs.items()}
+        assert torch.equal(outs["f32"][1].view(torch.int64), outs["bf16"][1].view(torch.int64))
+        assert torch.equal(outs["f32"][2], outs["u8"][2])
+        check((kind, L, t))
+    assert (envs["f32"].obs > 0).any() and (envs["u8"].obs == 255).any()
+    snap = envs["bf16"].state_dict()
+    envs["bf16"].load_state_dict(snap)                        # td_observe_as path
+    check("observe")
+    with pytest.raises(ValueError):
+        TDVecEnv("def", 12, 4, obs_format="bf16")
+    for e in envs.values():
+        e.close()
+
+
 def test_full_size_determinism_and_replayed_subset():
     """BASELINE.json config 2: 65,536 envs, Discrete actions; the first 256 envs replayed through the oracle;
     size-independent properties on the whole batch (broadcast planes equal the state, determinism)."""
