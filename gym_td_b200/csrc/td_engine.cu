@@ -496,7 +496,7 @@ __global__ void td_rng_pos_kernel(uint8_t *records, int record_bytes, int first,
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     td_env_header *h = reinterpret_cast<td_env_header *>(records + (size_t)(first + i) * record_bytes);
-    if (pos) { h->rng_pos = pos[i]; h->pad0 = 0; }   // pad0 = cached generator words: none valid any more
+    if (pos) { h->rng_pos = pos[i]; h->pad0 = 0; h->pad1 = 0; }   // pad0 / pad1 = cached generator words valid / consumed: none
     if (pos_out) pos_out[i] = h->rng_pos;
 }
 
@@ -1033,7 +1033,8 @@ extern "C" int td_set_state(td_handle *h, int first_env, int n, const void *blob
     for (int i = 0; i < n; ++i) {
         const td_env_header *hd = reinterpret_cast<const td_env_header *>(b + (size_t)i * h->record_bytes);
         if (hd->n_towers > TD_CAP_TOWERS || hd->n_enemies > TD_CAP_ENEMIES || hd->map_id < 0 ||
-            (h->n_maps > 0 && hd->map_id >= h->n_maps) || hd->rng_pos < 0 || hd->rng_pos > kMtWords)
+            (h->n_maps > 0 && hd->map_id >= h->n_maps) || hd->rng_pos < 0 || hd->rng_pos > kMtWords ||
+            hd->pad0 > h->rng_cache_words || hd->pad1 < 0 || hd->pad1 > hd->pad0)
             return fail(h, TD_E_INVALID, "td_set_state: record header out of range");
         const td_tower_rec *tw = reinterpret_cast<const td_tower_rec *>(b + (size_t)i * h->record_bytes + h->off_towers);
         for (int t = 0; t < hd->n_towers; ++t)

@@ -84,11 +84,15 @@ constexpr int kMtWords = 624;
 // behind the scratch area of a slice: the tower / enemy cells of the env before the step (incremental observation)
 constexpr int kOldListBytes = 16 + 4 * TD_CAP_TOWERS + 4 * TD_CAP_ENEMIES;
 constexpr int kTwistStageBytes = kMtWords * 4;   // staging area of the generator regeneration (tail of a slice)
+// Speculatively staged list prefixes.  Lists are short in practice (tools/state_hist.py: towers p99 = 10 in the
+// defender env, 11-13 in the attacker env whose scripted defender keeps building; live enemies p99 = 6): 12 towers
+// and 8 enemies cover almost every env and read 256 B less per env-step than 16 / 16 (def-small 0.2156 -> 0.2132 ms,
+// atk-small 0.2435 -> 0.2397 ms; 8 / 8 is best for def-small alone, 0.2126 ms, and neutral for atk-small).
 #ifndef TD_SPEC_TOWERS
-#define TD_SPEC_TOWERS 16
+#define TD_SPEC_TOWERS 12
 #endif
 #ifndef TD_SPEC_ENEMIES
-#define TD_SPEC_ENEMIES 16
+#define TD_SPEC_ENEMIES 8
 #endif
 constexpr int kSpecTowers = TD_SPEC_TOWERS;     // speculatively staged list prefixes
 constexpr int kSpecEnemies = TD_SPEC_ENEMIES;
@@ -169,6 +173,8 @@ struct Ctx {
     int mt_pos;
     int ck, cn;                 // consumed / valid words of the (tempered) word cache
     bool static_dirty;          // the record's static map was replaced (reset)
+    bool cache_dirty;           // the word cache changed this step (it goes back to the record)
+    bool cache_raw;             // ... by the asynchronous top-up: its words still have to be tempered
 
     __device__ __forceinline__ int L() const { return CELLS ? kL : pp->L; }
     __device__ __forceinline__ int ncells() const { return CELLS ? CELLS : pp->cells; }
@@ -271,6 +277,8 @@ __device__ __forceinline__ void ctx_bind(W &w, uint8_t *slice, const StepParams 
     w.mt_pos = 0;
     w.ck = 0; w.cn = 0;
     w.static_dirty = false;
+    w.cache_dirty = false;
+    w.cache_raw = false;
 }
 
 template <class W>
@@ -295,8 +303,8 @@ __device__ __forceinline__ void pull_header(W &w)
     w.flags = h->flags;
     w.fail = TD_FC_SUCCESS;
     w.mt_pos = h->rng_pos;
-    w.ck = 0;
-    w.cn = h->pad0;             // number of valid cached generator words
+    w.ck = h->pad1;             // cached generator words already consumed / valid (the cache holds tempered words)
+    w.cn = h->pad0;
 }
 
 template <class W>
@@ -315,6 +323,7 @@ __device__ __forceinline__ void push_header(W &w)
         h->flags = (uint8_t)w.flags;
         h->rng_pos = w.mt_pos;
         h->pad0 = (uint8_t)w.cn;
+        h->pad1 = w.ck;
     }
 }
 
@@ -365,10 +374,11 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y)
     return y;
 }
 
-// The generator words of a step are consumed from the record's word cache, tempered in place when the env is
-// loaded (temper_cache): a draw is one broadcast read from shared memory.  Only when a step needs more words than
-// the cache holds (the scripted defender's shuffle, a few percent of its steps) the out-of-line refill fetches the
-// next words from the generator state in HBM, twisting it when it is exhausted.
+// The generator words of a step are consumed from the record's word cache, which holds TEMPERED words: a draw is
+// one broadcast read from shared memory.  The cache is topped up behind the observation stores only when less
+// than half of it is left (refill / finish_refill: most steps neither read the generator state nor write the cache
+// back).  Only when a step needs more words than the cache holds (the scripted defender's shuffle, a few percent
+// of its steps) the out-of-line refill fetches them from the generator state in HBM, twisting it when exhausted.
 struct MtRefill { int cn, mt_pos; };
 __device__ __noinline__ MtRefill mt_refill(uint32_t *cache, uint32_t *mt, uint32_t *stage, int lane, int G, unsigned gmask,
                                            int mt_pos, int words)
@@ -392,9 +402,10 @@ __device__ __forceinline__ void mt_more_words(W &w)
     w.cn = r.cn;
     w.mt_pos = r.mt_pos;
     w.ck = 0;
+    w.cache_dirty = true;
 }
 
-// raw cached words -> tempered, in place (the cache is rewritten with the next step's raw words before write-back)
+// raw words just copied from the generator state -> tempered, in place
 template <class W>
 __device__ __forceinline__ void temper_cache(W &w)
 {
@@ -466,17 +477,26 @@ __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *re
     if (push) push_header(w);
     gsync(w);
     const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : w.hdr_bytes());
+    // the word cache block [kOffRngCache, hdr_bytes) goes back only when it was refilled
+    const int skip_lo = w.cache_dirty ? 0 : (kOffRngCache >> 4), skip_hi = w.cache_dirty ? 0 : (w.hdr_bytes() >> 4);
     if (!UNROLLED) {
-        warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
+        for (int q = w.lane; q < (head >> 4); q += W::G)
+            if (q < skip_lo || q >= skip_hi) reinterpret_cast<int4 *>(rec)[q] = reinterpret_cast<const int4 *>(w.slice)[q];
         warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane, W::G);
         warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane, W::G);
         return;
     }
     if (W::kCells > 0 && W::kRngWords > 0) {
         constexpr int kHeadMax = (kOffRngCache + 4 * W::kRngWords + 3 * W::kPad + kMapHdrBytes) / 16;   // = off_towers / 16
-        copy16_upto<kHeadMax, W::G>(rec, w.slice, head >> 4, w.lane);
+#pragma unroll
+        for (int k = 0; k < (kHeadMax + W::G - 1) / W::G; ++k) {
+            const int q = w.lane + W::G * k;
+            if (q < (head >> 4) && (q < skip_lo || q >= skip_hi))
+                reinterpret_cast<int4 *>(rec)[q] = reinterpret_cast<const int4 *>(w.slice)[q];
+        }
     } else {
-        warp_copy16(rec, w.slice, head >> 4, w.lane, W::G);
+        for (int q = w.lane; q < (head >> 4); q += W::G)
+            if (q < skip_lo || q >= skip_hi) reinterpret_cast<int4 *>(rec)[q] = reinterpret_cast<const int4 *>(w.slice)[q];
     }
     copy16_upto<TD_CAP_TOWERS, W::G>(rec + w.off_towers(), w.tw(), w.nt, w.lane);
     copy16_upto<(TD_CAP_ENEMIES * 3 + 1) / 2, W::G>(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane);
@@ -1529,8 +1549,9 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 #define TD_MIN_BLOCKS 6
 #endif
 #ifndef TD_MIN_BLOCKS_ATK
-#define TD_MIN_BLOCKS_ATK TD_MIN_BLOCKS
-#endif
+#define TD_MIN_BLOCKS_ATK 8      // 10x10 boards: the attacker env is latency-bound (scripted defender): 32 warps per SM at 64 registers
+#endif                           // (24 B of spills): 6 / 7 / 8 CTAs per SM = 0.2490 / 0.2440 / 0.2376 ms on B200; the other
+                                 // kinds gain nothing or lose (multi-action: +5 % at 7)
 
 // One env's rules for one step: load the record, apply the actions / scripted opponent, advance the board, emit
 // the per-env outputs, auto-reset.  Leaves the updated record in the slice and starts the asynchronous copy of
@@ -1569,7 +1590,6 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     gsync(w);
     finish_env_load(w, p, rec, device_opponent ? p.mt + (size_t)env * kMtWords : nullptr);
-    if (device_opponent) temper_cache(w);
     if (INC) {
         // remember where towers and enemies stand in the observation the caller's buffer still holds
         uint32_t *old = w.old_lists();
@@ -1649,7 +1669,9 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
     auto refill = [&]() {
         // Generator words for the next step: copied global -> shared straight into the slice's word cache (this
         // step's draws are done with it), asynchronously, so that no register waits for them behind the observation.
-        if (w.mt != nullptr) {
+        if (w.mt != nullptr && w.cn - w.ck < (w.rng_words() >> 1)) {
+            w.cache_dirty = true;
+            w.cache_raw = true;
             w.ck = 0;
             w.cn = min(w.rng_words(), max(kMtWords - w.mt_pos, 0));
             constexpr int kRefill = (W::kRngWords + GW - 1) / GW;
@@ -1744,7 +1766,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
 // INC: the observation is an in-place update of the previous one (td_step_io.obs_incremental, vouched for by the
 // engine); a separate instantiation, so that the full-write kernels carry none of its code.
 template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC, class OT = float>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, KIND == TD_KIND_ATK ? TD_MIN_BLOCKS_ATK : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (KIND == TD_KIND_ATK && CELLS == 100) ? TD_MIN_BLOCKS_ATK : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);
@@ -1764,6 +1786,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, KIND == TD_KIND_ATK ? TD_MI
     // kernels keep the record for last: 0.2175 vs 0.2206 ms on def-small.
     if (INC) {
         asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (w.cache_raw) { gsync(w); temper_cache(w); }
         store_env<true>(w, p, rec, dirty, false);
     }
     if (p.io.obs_dev) {
@@ -1778,7 +1801,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, KIND == TD_KIND_ATK ? TD_MI
         }
     }
     if (!INC) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next step's generator words are in the slice
+        asm volatile("cp.async.wait_group 0;" ::: "memory");      // the next steps' generator words are in the slice
+        if (w.cache_raw) { gsync(w); temper_cache(w); }
         store_env<(KIND == TD_KIND_ATK)>(w, p, rec, dirty, false);
     }
 }

@@ -197,11 +197,11 @@ typedef struct td_env_header {
     uint8_t n_towers;
     uint8_t n_enemies;
     uint8_t flags;              /* bit0 enemy overflow, bit1 tower overflow (sticky) */
-    uint8_t pad0;
+    uint8_t pad0;               /* internal: valid words of the record's generator word cache */
     uint16_t ep_kills;
     uint16_t ep_leaks;
     int32_t rng_pos;            /* position in the opponent MT19937 state (0..624) */
-    int32_t pad1;
+    int32_t pad1;               /* internal: consumed words of that cache */
     int32_t pad2;
 } td_env_header;                /* 64 bytes */
 
