@@ -840,10 +840,10 @@ static bool host_pointer_is_pinned(const void *p)
 static int host_chunk_count(const td_handle *h, const td_host_io *host)
 {
     // measured on B200 (def-small, 65,536 envs, tools/e2e_sweep.py): every extra chained chunk costs ~10 us of kernel
-    // boundary, more than the copy time it hides (1 / 2 / 4 chunks: 0.290 / 0.301 / 0.326 ms per step), so one chunk
-    // is the default; only the PCIe-bound variant that also ships the observation gains from cutting
-    int chunks = h->host_chunks;
-    if (chunks <= 0) chunks = host->obs_host ? 8 : 1;
+    // boundary, more than the copy time it hides (1 / 2 / 4 chunks: 0.290 / 0.301 / 0.326 ms per step before the
+    // outputs became zero-copy, 0.242 / 0.252 / 0.269 after), so one chunk is the default
+    (void)host;
+    const int chunks = h->host_chunks > 0 ? h->host_chunks : 1;
     return std::max(1, std::min(chunks, h->n_envs));
 }
 
@@ -914,7 +914,9 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
     const int chunks = host_chunk_count(h, host);
     h->obs_synced = nullptr;                                    // until every chunk was launched
 
-    bool use_graph = h->host_graph != 0;
+    // the PCIe-bound variant that also ships the observation (1.2 GB per step at 65,536 envs) gains nothing from a
+    // graph and measured slower through graph memcpy nodes (1.9e6 vs 3.1e6 env-steps/s): plain stream copies
+    bool use_graph = h->host_graph != 0 && host->obs_host == nullptr;
     if (use_graph) {
         // a graph keeps raw host addresses: only page-locked buffers qualify
         const void *hp[] = {host->def_action_host, host->atk_action_host, host->opponent_host, host->obs_host,

@@ -1551,7 +1551,8 @@ extern __shared__ __align__(16) uint8_t td_smem[];
 #ifndef TD_MIN_BLOCKS_ATK
 #define TD_MIN_BLOCKS_ATK 8      // 10x10 boards: the attacker env is latency-bound (scripted defender): 32 warps per SM at 64 registers
 #endif                           // (24 B of spills): 6 / 7 / 8 CTAs per SM = 0.2490 / 0.2440 / 0.2376 ms on B200; the other
-                                 // kinds gain nothing or lose (multi-action: +5 % at 7)
+                                 // kinds gain nothing or lose (multi-action: +5 % at 7); its in-place-observation variant is
+                                 // best at 7 (0.2075 vs 0.2195 ms at 8)
 
 // One env's rules for one step: load the record, apply the actions / scripted opponent, advance the board, emit
 // the per-env outputs, auto-reset.  Leaves the updated record in the slice and starts the asynchronous copy of
@@ -1766,7 +1767,7 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
 // INC: the observation is an in-place update of the previous one (td_step_io.obs_incremental, vouched for by the
 // engine); a separate instantiation, so that the full-write kernels carry none of its code.
 template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC, class OT = float>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (KIND == TD_KIND_ATK && CELLS == 100) ? TD_MIN_BLOCKS_ATK : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (KIND == TD_KIND_ATK && CELLS == 100) ? (INC ? 7 : TD_MIN_BLOCKS_ATK) : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW, lane = threadIdx.x & (GW - 1);

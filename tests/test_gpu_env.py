@@ -350,6 +350,35 @@ def test_reduced_precision_observation_planes(kind, L):
         e.close()
 
 
+def test_attacker_action_at_an_unaligned_address():
+    """The (3, 8) int64 attacker action normally rides in with the record as 16-byte asynchronous copies; a tensor
+    that starts 8 bytes off a 16-byte boundary takes the plain-load path.  Same results either way."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    N = 257
+    envs = [TDVecEnv(k, 10, N, seed=4, auto_reset=True) for k in ("atk", "atk", "2p", "2p")]
+    for e in envs:
+        e.reset()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    raw = torch.zeros(N * 24 + 1, dtype=torch.int64, device="cuda")
+    off = raw[1:].view(N, 3, 8)
+    assert off.data_ptr() % 16 == 8 and off.is_contiguous()
+    for t in range(80):
+        a = torch.randint(0, 5, (N, 3, 8), dtype=torch.int64, device="cuda", generator=g)
+        d = torch.randint(0, 601, (N,), dtype=torch.int64, device="cuda", generator=g)
+        off.copy_(a)
+        o1, r1, d1, i1 = envs[0].step(a)
+        o2, r2, d2, i2 = envs[1].step(off)
+        assert torch.equal(o1.view(torch.int32), o2.view(torch.int32)) and torch.equal(r1.view(torch.int64), r2.view(torch.int64))
+        assert torch.equal(i1["RealAction"], i2["RealAction"]) and torch.equal(i1["FailCode"], i2["FailCode"])
+        o3, r3, d3, i3 = envs[2].step({"Attacker": a, "Defender": d})
+        o4, r4, d4, i4 = envs[3].step({"Attacker": off, "Defender": d})
+        assert torch.equal(o3.view(torch.int32), o4.view(torch.int32)) and torch.equal(r3.view(torch.int64), r4.view(torch.int64))
+        assert torch.equal(i3["RealAction"]["Attacker"], i4["RealAction"]["Attacker"])
+    for e in envs:
+        e.close()
+
+
 def test_full_size_determinism_and_replayed_subset():
     """BASELINE.json config 2: 65,536 envs, Discrete actions; the first 256 envs replayed through the oracle;
     size-independent properties on the whole batch (broadcast planes equal the state, determinism)."""
