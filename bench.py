@@ -486,7 +486,36 @@ def main():
     if args.replay > 0:
         replay = replay_check(torch, dist, env, action, args.replay, args.replay_steps, world, dev)
     env.close()
-    del env, def_pool, atk_pool
+    del env
+    torch.cuda.empty_cache()
+
+    # Opt-in reduced-precision observation planes (td_step_io.obs_format): same layout, bf16 / u8
+    # elements.  Reported next to the headline like the in-place update; never the headline.
+    reduced = None
+    if rank == 0 and world == 1 and not multi and L in (10, 20, 30):
+        reduced = {}
+        for fmt in ("bf16", "u8"):
+            e2 = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
+                          env_offset=D.rank_env_offset(rank), obs_format=fmt)
+            e2.reset()
+            for k in range(min(args.preroll, 400) + args.warmup):
+                e2.step(action(k))
+            torch.cuda.synchronize()
+            s3, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s3.record()
+            for k in range(args.steps):
+                e2.step(action(k))
+            e3.record()
+            torch.cuda.synchronize()
+            ms3 = s3.elapsed_time(e3) / args.steps
+            reduced[fmt] = {"ms_per_step": ms3, "value": n_envs / (ms3 * 1e-3), "unit": UNIT,
+                            "obs_bytes_per_env_step": 45 * L * L * e2.obs.element_size()}
+            e2.close()
+            del e2
+            torch.cuda.empty_cache()
+        reduced["note"] = ("observation written as bfloat16 (round-to-nearest-even of the float32 value) / uint8 "
+                           "(rint(min(255 v, 255))); fewer bytes, not the reference tensor: not comparable to the headline")
+    del def_pool, atk_pool
     torch.cuda.empty_cache()
 
     # BASELINE.json configs 3-5 next to the headline (N = 1 by default: they would triple every SCALE run)
@@ -519,6 +548,8 @@ def main():
         line["host_cores_per_rank"] = cores_per_rank
     if inc is not None:
         line["incremental_obs"] = inc
+    if reduced:
+        line["reduced_precision_obs"] = reduced
     if e2e is not None:
         line["e2e"] = e2e
         if e2e_obs is not None:

@@ -427,6 +427,7 @@ template <class W>
 __device__ __forceinline__ uint32_t mt_next(W &w)
 {
     if (__builtin_expect(w.ck >= w.cn, 0)) mt_more_words(w);
+    TD_CHECK(w, w.ck >= 0 && w.ck < w.cn && w.cn <= w.rng_words() && w.mt_pos < kMtWords);
     const uint32_t r = w.rng_cache()[w.ck];
     ++w.ck;
     ++w.mt_pos;
@@ -554,6 +555,7 @@ __device__ __forceinline__ void py_shuffle_u16(W &w, uint16_t *list, int n)
     int i = n - 1;
     while (i >= 1) {
         if (w.ck >= w.cn) mt_more_words(w);
+        TD_CHECK(w, w.cn <= w.rng_words() && w.mt_pos + (w.cn - w.ck) <= kMtWords);
         int k = w.ck;
         if (w.lane == 0) {
             const uint32_t *words = w.rng_cache();
