@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libtd_b200.so")
 SOURCES = ["td_engine.cu", "td_mapgen.cpp"]
-DEPS = SOURCES + ["td_kernels.cuh", "td_rollout.cuh", os.path.join("..", "..", "include", "td_b200.h")]
+DEPS = SOURCES + ["td_kernels.cuh", "td_common.cuh", "td_rng.cuh", "td_rules.cuh", "td_obs.cuh", "td_rollout.cuh",
+                  os.path.join("..", "..", "include", "td_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC,-pthread"]

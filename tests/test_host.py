@@ -52,7 +52,7 @@ def test_rank_env_ranges_are_disjoint():
 
 def test_distance_plane_division_is_correctly_rounded_for_every_operand():
     """The step kernel writes dist / (max dist + 1) with a hand-rolled float32 division (SmallDiv in
-    csrc/td_kernels.cuh: refined reciprocal, quotient, exact remainder, correction).  Exact rational
+    csrc/td_obs.cuh: refined reciprocal, quotient, exact remainder, correction).  Exact rational
     arithmetic with round-to-nearest-even shows it returns the IEEE quotient for every 0 <= a <= 255,
     1 <= b <= 256 and for any hardware reciprocal within one ulp of 1 / b."""
     from fractions import Fraction

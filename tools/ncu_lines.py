@@ -16,7 +16,11 @@ import sys
 import tempfile
 
 
+CSRC_FILES = ("td_common.cuh", "td_rng.cuh", "td_rules.cuh", "td_obs.cuh", "td_kernels.cuh")
+
+
 def sass_lines(lib, kernel):
+    """SASS offset -> (source file base name, line) of one kernel, from nvdisasm -g."""
     tmp = tempfile.mkdtemp()
     subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
     out = {}
@@ -33,7 +37,7 @@ def sass_lines(lib, kernel):
                 continue
             m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
             if m:
-                cur = int(m.group(2))
+                cur = (m.group(1).split("/")[-1], int(m.group(2)))
                 continue
             m = re.match(r"\s*/\*([0-9a-f]{4,})\*/", ln)
             if m:
@@ -63,30 +67,41 @@ def main():
         per_line_s[ln] += int(r[si] or 0)
     ti, ts = sum(per_line_i.values()), sum(per_line_s.values())
     print("kernel:", names[0][:80], "sass:", len(data), "inst:", ti, "samples:", ts)
-    src = open(os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc", "td_kernels.cuh")).read().splitlines()
+    csrc = os.path.join(os.path.dirname(os.path.abspath(lib)), "csrc")
+    src = {f: open(os.path.join(csrc, f)).read().splitlines() for f in CSRC_FILES}
     print("-- top lines by stall samples")
-    for ln, s in per_line_s.most_common(top):
-        text = src[ln - 1].strip()[:100] if ln and ln <= len(src) else "?"
-        print("%5s  samp %5.1f%%  inst %5.1f%%  | %s" % (ln, 100.0 * s / ts, 100.0 * per_line_i[ln] / ti, text))
+    for key, s_ in per_line_s.most_common(top):
+        f, ln = key if key else ("?", 0)
+        text = src[f][ln - 1].strip()[:100] if f in src and 0 < ln <= len(src[f]) else "?"
+        print("%-14s %5s  samp %5.1f%%  inst %5.1f%%  | %s" % (f, ln, 100.0 * s_ / ts, 100.0 * per_line_i[key] / ti, text))
     # coarse phases by function: find "__device__ ... name(" definitions
-    funcs = []
-    for n, t in enumerate(src, 1):
-        m = re.match(r"\s*(?:template.*>\s*)?(?:__global__|__device__).*?\b(\w+)\s*\(", t)
-        if m and not t.strip().endswith(";"):
-            funcs.append((n, m.group(1)))
-    def func_of(ln):
+    funcs = {}
+    for f, text in src.items():
+        funcs[f] = []
+        for n, t in enumerate(text, 1):
+            m = re.match(r"\s*(?:template.*>\s*)?(?:__global__|__device__).*?\b(\w+)\s*\(", t)
+            if m and not t.strip().endswith(";"):
+                funcs[f].append((n, m.group(1)))
+
+    def func_of(key):
+        if not key:
+            return "?"
+        f, ln = key
+        if f not in funcs:
+            return "<" + f + ">"
         name = "?"
-        for n, f in funcs:
-            if ln is not None and n <= ln:
-                name = f
+        for n, fn in funcs[f]:
+            if n <= ln:
+                name = fn
         return name
+
     fi, fs = collections.Counter(), collections.Counter()
-    for ln in per_line_i:
-        fi[func_of(ln)] += per_line_i[ln]
-        fs[func_of(ln)] += per_line_s[ln]
+    for key in per_line_i:
+        fi[func_of(key)] += per_line_i[key]
+        fs[func_of(key)] += per_line_s[key]
     print("-- per function")
-    for f, s in fs.most_common():
-        print("%-22s samp %5.1f%%  inst %5.1f%%  (%d warp-inst)" % (f, 100.0 * s / ts, 100.0 * fi[f] / ti, fi[f]))
+    for f, s_ in fs.most_common():
+        print("%-22s samp %5.1f%%  inst %5.1f%%  (%d warp-inst)" % (f, 100.0 * s_ / ts, 100.0 * fi[f] / ti, fi[f]))
 
 
 if __name__ == "__main__":

@@ -3,11 +3,12 @@
     cuobjdump -xelf all gym_td_b200/libtd_b200.so && nvdisasm -g td_engine.sm_100a.cubin > all.txt
     python tools/sass_by_function.py all.txt 'td_step_kernelILi1ELb0ELi100'
 """
+import os
 import re
 import sys
 from collections import Counter
 
-SRC = "gym_td_b200/csrc/td_kernels.cuh"
+SRCS = ["gym_td_b200/csrc/%s" % f for f in ("td_common.cuh", "td_rng.cuh", "td_rules.cuh", "td_obs.cuh", "td_kernels.cuh")]
 
 
 def function_spans(path):
@@ -27,7 +28,7 @@ def function_spans(path):
 
 def main():
     dis, key = sys.argv[1], sys.argv[2]
-    spans = function_spans(SRC)
+    spans = {os.path.basename(f): function_spans(f) for f in SRCS}
     counts, cur, active, total = Counter(), "?", False, 0
     for ln in open(dis):
         if ln.startswith("//---") and ".text." in ln:
@@ -38,9 +39,10 @@ def main():
             continue
         m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
         if m:
-            if m.group(1).endswith("td_kernels.cuh"):
+            base = m.group(1).split("/")[-1]
+            if base in spans:
                 n = int(m.group(2))
-                cur = next((f for a, b, f in spans if a <= n <= b), "line %d" % n)
+                cur = next((f for a, b, f in spans[base] if a <= n <= b), "%s line %d" % (base, n))
             else:
                 cur = "<" + m.group(1).split("/")[-1] + ">"
             continue
