@@ -347,10 +347,28 @@ __device__ __forceinline__ void load_env(W &w, const StepParams &p, const uint8_
 // UNROLLED: predicated single-pass copies instead of loops -- 45 fewer instructions per env-step.  Measured on
 // B200: attacker env 0.291 -> 0.273 ms, in-place observation update (def-small) 0.191 -> 0.167 ms, but the
 // full-write defender step 0.2175 -> 0.2220 ms (same box, twice), so the caller chooses per kernel variant.
+// List write-back granularity (experiment): 1 = whole 32-byte sectors (the dead slot behind an odd list end goes back
+// as zeros), so that no partial-sector write reaches the ECC-protected HBM as a read-modify-write.  Measured on
+// B200: no difference (def-small 0.2160 vs 0.2158 ms, atk-small 0.2365 vs 0.2379) -- L2 merges them; off.
+#ifndef TD_WB_SECTORS
+#define TD_WB_SECTORS 0
+#endif
+#if TD_WB_SECTORS
+#define TD_WB_ROUND(n16) (((n16) + 1) & ~1)
+#else
+#define TD_WB_ROUND(n16) (n16)
+#endif
 template <bool UNROLLED = false, class W>
 __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *rec, bool map6_dirty, bool push = true)
 {
     if (push) push_header(w);
+#if TD_WB_SECTORS
+    if (w.lane == 0) {          // the dead slot that rides along in the last sector goes back as zeros (deterministic)
+        const int e16 = (w.ne * 3 + 1) >> 1;
+        if (w.nt & 1) reinterpret_cast<int4 *>(w.tw())[w.nt] = make_int4(0, 0, 0, 0);
+        if (e16 & 1) reinterpret_cast<int4 *>(w.en())[e16] = make_int4(0, 0, 0, 0);
+    }
+#endif
     gsync(w);
     const int head = w.static_dirty ? w.off_towers() : (map6_dirty ? w.off_static() : w.hdr_bytes());
     // the word cache block [kOffRngCache, hdr_bytes) goes back only when it was refilled
@@ -358,8 +376,8 @@ __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *re
     if (!UNROLLED) {
         for (int q = w.lane; q < (head >> 4); q += W::G)
             if (q < skip_lo || q >= skip_hi) reinterpret_cast<int4 *>(rec)[q] = reinterpret_cast<const int4 *>(w.slice)[q];
-        warp_copy16(rec + w.off_towers(), w.tw(), w.nt, w.lane, W::G);
-        warp_copy16(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane, W::G);
+        warp_copy16(rec + w.off_towers(), w.tw(), TD_WB_ROUND(w.nt), w.lane, W::G);
+        warp_copy16(rec + w.off_enemies(), w.en(), TD_WB_ROUND((w.ne * 3 + 1) >> 1), w.lane, W::G);
         return;
     }
     if (W::kCells > 0 && W::kRngWords > 0) {
@@ -374,8 +392,8 @@ __device__ __forceinline__ void store_env(W &w, const StepParams &p, uint8_t *re
         for (int q = w.lane; q < (head >> 4); q += W::G)
             if (q < skip_lo || q >= skip_hi) reinterpret_cast<int4 *>(rec)[q] = reinterpret_cast<const int4 *>(w.slice)[q];
     }
-    copy16_upto<TD_CAP_TOWERS, W::G>(rec + w.off_towers(), w.tw(), w.nt, w.lane);
-    copy16_upto<(TD_CAP_ENEMIES * 3 + 1) / 2, W::G>(rec + w.off_enemies(), w.en(), (w.ne * 3 + 1) >> 1, w.lane);
+    copy16_upto<TD_CAP_TOWERS, W::G>(rec + w.off_towers(), w.tw(), TD_WB_ROUND(w.nt), w.lane);
+    copy16_upto<(TD_CAP_ENEMIES * 3 + 1) / 2, W::G>(rec + w.off_enemies(), w.en(), TD_WB_ROUND((w.ne * 3 + 1) >> 1), w.lane);
 }
 
 // TDGymBasic.reset (:37-55) + TDBoard.__init__ (:63-79): fresh episode on map `map_id`.

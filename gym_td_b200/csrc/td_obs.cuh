@@ -242,6 +242,7 @@ __device__ __forceinline__ void obs_sparse(W &w, OT *o)
         obs_store1(o, (size_t)(17 + (T.type_lv & 3)) * cells + T.loc, 1.f);
     }
     if (one_pass) {
+        if (ne == 0) return;                                     // no live enemy (about half of all env-steps): nothing to fold
         // lanes of one (cell, type) group find each other with one match instruction; every lane then folds its
         // group's ratios in list order (ascending lane): as many rounds as the largest group has members
         const bool have = lane < ne;
