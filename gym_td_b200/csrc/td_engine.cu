@@ -235,11 +235,22 @@ static int step_group_width(const td_handle *h) { return h->L == 10 ? TD_GROUP_S
 // three CTAs (12 warps = 12 open observation streams) share an SM instead of six: HBM write efficiency falls
 // with the number of long streams written side by side (tools/storebench_sized.cu, test F: 162 KB regions at
 // 4 / 12 / 24 warps per SM -> 7.0 / 6.3 / 5.75 TB/s), and the rules of a large board are a small part of the step.
+static bool large_observation(const td_handle *h) { return (size_t)TD_NCHANNELS * h->cells * sizeof(float) >= 128 * 1024; }
+
 static size_t step_smem_bytes(const td_handle *h)
 {
     size_t bytes = (size_t)(kWarpsPerCta * 32 / step_group_width(h)) * h->smem_per_warp;
-    if ((size_t)TD_NCHANNELS * h->cells * sizeof(float) >= 128 * 1024) bytes = std::max(bytes, (size_t)75 * 1024);
+    if (large_observation(h)) bytes = std::max(bytes, (size_t)75 * 1024);
     return bytes;
+}
+
+// Warps per step CTA.  The full-write kernels are insensitive to it (1 / 2 / 4 warps: def-small 0.2131 / 0.2129 /
+// 0.2131 ms, 8 warps 0.2180); the in-place observation update is latency-bound and gains from single-warp CTAs,
+// whose slots are re-filled as soon as ONE env is done (def-small 0.1765 -> 0.1580 ms, atk-small 0.2119 -> 0.1973).
+static int step_warps_per_cta(const td_handle *h, bool incremental)
+{
+    // (10x10 boards only: at 20x20 it changes nothing, 0.1921 vs 0.1916 ms)
+    return incremental && h->L == 10 && step_group_width(h) == 32 ? 1 : kWarpsPerCta;
 }
 
 static int step_variant(int kind, bool multi)
@@ -631,9 +642,10 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
     p.io = *io;
     p.env_begin = begin;
     p.n_envs = begin + count;
-    const int per_cta = kWarpsPerCta * 32 / step_group_width(h);         // game instances per CTA
-    const int grid = (count + per_cta - 1) / per_cta, block = kWarpsPerCta * 32;
-    size_t smem = step_smem_bytes(h);
+    const int wpc = step_warps_per_cta(h, incremental);
+    const int per_cta = wpc * 32 / step_group_width(h);                  // game instances per CTA
+    const int grid = (count + per_cta - 1) / per_cta, block = wpc * 32;
+    size_t smem = wpc == kWarpsPerCta ? step_smem_bytes(h) : (size_t)per_cta * h->smem_per_warp;
     if (h->step_smem_kb > 0 && (size_t)h->step_smem_kb * 1024 > smem) {       // experiments (td_set_option)
         smem = (size_t)h->step_smem_kb * 1024;
         for_each_step_kernel(h, incremental, [&](auto kernel) { return allow_smem(kernel, smem); });

@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, (KIND == TD_KIND_ATK && CEL
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW;
-    const int env = p.env_begin + blockIdx.x * (kWarpsPerCta * 32 / GW) + group;
+    const int env = p.env_begin + blockIdx.x * (blockDim.x / GW) + group;      // any CTA size up to kWarpsPerCta warps
     if (env >= p.n_envs) return;
     constexpr int RC = KIND == TD_KIND_ATK ? kRngCacheAtk : kRngCacheDef;
     Ctx<CELLS, GW, RC> w;

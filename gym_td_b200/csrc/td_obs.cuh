@@ -234,6 +234,9 @@ __device__ __forceinline__ void obs_sparse(W &w, OT *o)
         }
     }
     gsync(w);   // also orders the dense stores above before the sparse stores below
+#ifdef TD_EXP_NO_SPARSE      // timing experiment only (wrong observations): what do the sparse fix-ups cost?
+    return;
+#endif
     if (lane == 0) obs_store1(o, (size_t)4 * cells + w.mh()->end, 1.f);
     if (lane < w.mh()->num_roads) obs_store1(o, (size_t)(6 + lane) * cells + w.mh()->start[lane], 1.f);
     for (int t = lane; t < w.nt; t += W::G) {
