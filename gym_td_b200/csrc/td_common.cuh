@@ -44,6 +44,11 @@ __device__ __forceinline__ void td_st_first(float *a, float v)
 #ifndef TD_WARPS_PER_CTA
 #define TD_WARPS_PER_CTA 4
 #endif
+// Leading bytes of every env record that are loaded with an L2 evict_last policy (0 = none; >= 4096 = the whole
+// speculative load).  See DESIGN.md 7.2(c).
+#ifndef TD_L2_KEEP_BYTES
+#define TD_L2_KEEP_BYTES 0
+#endif
 
 
 namespace td {
@@ -231,6 +236,22 @@ __device__ __forceinline__ void warp_copy16(void *dst, const void *src, int n16,
 
 // global -> shared, 16 bytes per lane per instruction, asynchronous (LDGSTS): every segment of a stage
 // is in flight at once and no register is held while the data travels.
+// The same with an L2 evict_last policy on units [0, keep16): those lines keep their place in L2 under the observation
+// write stream (tools/storebench_l2.cu: lines brought in evict_last stay resident, later plain hits keep them).
+__device__ __forceinline__ void async_copy16_keep(void *smem_dst, const void *gmem_src, int n16, int keep16, int lane, int stride)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const char *s = reinterpret_cast<const char *>(gmem_src);
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    for (int q = lane; q < n16; q += stride) {
+        if (q < keep16)
+            asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d + 16u * q), "l"(s + 16 * q), "l"(pol) : "memory");
+        else
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d + 16u * q), "l"(s + 16 * q) : "memory");
+    }
+}
+
 __device__ __forceinline__ void async_copy16(void *smem_dst, const void *gmem_src, int n16, int lane, int stride)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -314,8 +335,16 @@ __device__ __forceinline__ void push_header(W &w)
 template <class W>
 __device__ __forceinline__ void issue_env_load(W &w, const uint8_t *rec)
 {
+#if TD_L2_KEEP_BYTES > 0
+    async_copy16_keep(w.slice, rec, (w.off_towers() + kSpecTowers * kTowerBytes) >> 4, TD_L2_KEEP_BYTES >> 4, w.lane, W::G);
+#else
     async_copy16(w.slice, rec, (w.off_towers() + kSpecTowers * kTowerBytes) >> 4, w.lane, W::G);
+#endif
+#if TD_L2_KEEP_BYTES >= 4096
+    async_copy16_keep(w.en(), rec + w.off_enemies(), (kSpecEnemies * kEnemyBytes) >> 4, 4096, w.lane, W::G);
+#else
     async_copy16(w.en(), rec + w.off_enemies(), (kSpecEnemies * kEnemyBytes) >> 4, w.lane, W::G);
+#endif
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
