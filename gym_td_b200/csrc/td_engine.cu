@@ -250,12 +250,27 @@ static size_t step_smem_bytes(const td_handle *h)
 static int step_warps_per_cta(const td_handle *h, bool incremental)
 {
     // (10x10 boards only: at 20x20 it changes nothing, 0.1921 vs 0.1916 ms)
+#ifdef TD_ATK_WARPS_PER_CTA       // experiment: CTA size of the full-write attacker kernel on 10x10 boards (1 / 2 / 4 warps:
+                                  // 0.2369 / 0.2384 / 0.2390 ms before the OPP specialisation, 0.2293 vs 0.2287 ms after it)
+    if (!incremental && h->kind == TD_KIND_ATK && h->L == 10 && step_group_width(h) == 32) return TD_ATK_WARPS_PER_CTA;
+#endif
     return incremental && h->L == 10 && step_group_width(h) == 32 ? 1 : kWarpsPerCta;
 }
 
-static int step_variant(int kind, bool multi)
+// The scripted opponent of level 1 draws from the device generator and no host-resolved opponent input is set:
+// the case the specialised kernels (variants 5-7, OPP = 1) are compiled for.
+static bool scripted_lv1_on_device(const td_handle *h, const td_step_io *io)
 {
-    return kind == TD_KIND_DEF ? (multi ? 1 : 0) : kind == TD_KIND_ATK ? 2 : (multi ? 4 : 3);
+    return h->kind != TD_KIND_2P && h->difficulty == 1 && h->opponent_seeded && h->mt != nullptr &&
+           io->opponent_dev == nullptr && io->opponent_cluster_dev == nullptr &&
+           (h->kind != TD_KIND_ATK || io->def_action_dev == nullptr);
+}
+
+static int step_variant(const td_handle *h, const td_step_io *io)
+{
+    const bool multi = io->multi_action != 0;
+    if (scripted_lv1_on_device(h, io)) return h->kind == TD_KIND_DEF ? (multi ? 6 : 5) : 7;
+    return h->kind == TD_KIND_DEF ? (multi ? 1 : 0) : h->kind == TD_KIND_ATK ? 2 : (multi ? 4 : 3);
 }
 
 template <int CELLS, int NCHUNK, int GW, bool INC, typename F> static cudaError_t for_each_kind(F f)
@@ -265,7 +280,11 @@ template <int CELLS, int NCHUNK, int GW, bool INC, typename F> static cudaError_
     if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
     if ((e = f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
     if ((e = f(td_step_kernel<TD_KIND_2P, false, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
-    return f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK, GW, INC>);
+    if ((e = f(td_step_kernel<TD_KIND_2P, true, CELLS, NCHUNK, GW, INC>)) != cudaSuccess) return e;
+    // variants 5-7: the default scripted opponent (level 1 on the device generator) known at compile time
+    if ((e = f(td_step_kernel<TD_KIND_DEF, false, CELLS, NCHUNK, GW, INC, float, 1>)) != cudaSuccess) return e;
+    if ((e = f(td_step_kernel<TD_KIND_DEF, true, CELLS, NCHUNK, GW, INC, float, 1>)) != cudaSuccess) return e;
+    return f(td_step_kernel<TD_KIND_ATK, false, CELLS, NCHUNK, GW, INC, float, 1>);
 }
 
 // incremental: the in-place observation update (specialised board sizes only; others always write in full)
@@ -651,7 +670,7 @@ static int launch_step(td_handle *h, const td_step_io *io, int begin, int count,
         for_each_step_kernel(h, incremental, [&](auto kernel) { return allow_smem(kernel, smem); });
     }
     const bool reduced = io->obs_format != TD_OBS_F32 && io->obs_dev != nullptr;
-    const int want = reduced ? h->kind : step_variant(h->kind, io->multi_action != 0);
+    const int want = reduced ? h->kind : step_variant(h, io);
     int seen = 0;
     auto launch = [&](auto kernel) {
         if (seen++ != want) return cudaSuccess;
