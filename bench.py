@@ -466,10 +466,12 @@ def main():
         h2d, d2h = env.host_bytes_per_step(False)
         e2e = {"value": n_envs * n_gpus * ke / median(walls), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "steps": ke, "timed_repeats": len(walls),
-               "note": "td_step_host: pinned host actions -> device, fused step, reward/done/win/allow/"
-                       "RealAction/FailCode -> host, stream sync every step (host wall clock, max over ranks, median "
-                       "of the repeats); the observation stays in HBM for the on-device learner (see e2e_host_obs "
-                       "for the variant that also copies it)"}
+               "note": "td_step_host: actions in pinned host memory -> device (8-byte Discrete actions are read by the "
+                       "step kernel over PCIe, larger ones by copy nodes in front of independent chunk kernels), fused "
+                       "step, reward/done/win/allow/RealAction/FailCode -> pinned host memory (one packed record per env, "
+                       "stored by the kernel), stream sync every step (host wall clock, max over ranks, median of the "
+                       "repeats); the observation stays in HBM for the on-device learner (see e2e_host_obs for the "
+                       "variant that also copies it)"}
         if rank == 0 and world == 1:
             ko = 5
             env.step_host(haction(0), want_obs=True)

@@ -14,6 +14,8 @@
 
 using namespace td;
 
+struct HostCopy { void *dst; const void *src; size_t bytes; };     // one copy of td_step_host (either direction)
+
 struct td_handle {
     int device, kind, L, cells, cells_pad, n_envs;
     int n_maps, map_stride, difficulty;
@@ -37,7 +39,13 @@ struct td_handle {
     int host_chunks;               // 0 = automatic
     int host_graph;                // 1 = graph launch (default), 0 = plain stream launches
     int step_smem_kb, obs_smem_kb; // experiments (td_set_option): lower the residency of the step / observe kernels
+    bool generic_kernels;          // td_set_option: never pick the opponent-specialised step kernels
+    bool host_chain;               // td_step_host graph: chunk kernels chained, or independent branches (default)
+    int host_first_chunk;          // td_step_host: envs in the first chunk (chunks grow x3); 0 = equal chunks, -1 = automatic
     unsigned long long cfg_generation;
+    std::vector<unsigned char> host_key;   // td_step_host: lookup key of the call in progress
+    std::vector<HostCopy> host_in, host_out;   // td_step_host: copy lists of the call in progress
+    int host_zero_copy;            // td_step_host inputs read by the kernel from host memory: -1 automatic (8-byte actions), 0 never, 1 always
     td_config cfg;
     DevConfig dev_cfg;             // derived tables of cfg; copied into the parameters of every launch (per handle)
     std::string err;
@@ -261,7 +269,7 @@ static int step_warps_per_cta(const td_handle *h, bool incremental)
 // the case the specialised kernels (variants 5-7, OPP = 1) are compiled for.
 static bool scripted_lv1_on_device(const td_handle *h, const td_step_io *io)
 {
-    return h->kind != TD_KIND_2P && h->difficulty == 1 && h->opponent_seeded && h->mt != nullptr &&
+    return !h->generic_kernels && h->kind != TD_KIND_2P && h->difficulty == 1 && h->opponent_seeded && h->mt != nullptr &&
            io->opponent_dev == nullptr && io->opponent_cluster_dev == nullptr &&
            (h->kind != TD_KIND_ATK || io->def_action_dev == nullptr);
 }
@@ -363,7 +371,8 @@ extern "C" int td_create(const td_config *cfg, int env_kind, int map_size, int n
     h->records = nullptr; h->maps = nullptr; h->mt = nullptr; h->stats = nullptr; h->stats_dev = nullptr;
     h->opponent_seeded = false; h->steps = 0;
     h->host_graph_clock = 0; h->host_stream = nullptr; h->host_chunks = 0; h->host_graph = 1;
-    h->step_smem_kb = 0; h->obs_smem_kb = 0; h->cfg_generation = 0;
+    h->step_smem_kb = 0; h->obs_smem_kb = 0; h->cfg_generation = 0; h->generic_kernels = false;
+    h->host_chain = false; h->host_first_chunk = -1; h->host_zero_copy = -1;
     td_config def;
     if (!cfg) { td_default_config(&def); cfg = &def; }
     int rc = validate_config(h, cfg);
@@ -807,7 +816,6 @@ extern "C" int td_observe_snapshot(td_handle *h, const void *records_dev, int n,
 // kernels before it and its output copy the kernels after it (instances are independent, so a chunk is a
 // complete unit of work).  The list is either instantiated once as a CUDA graph and replayed with one launch
 // (default), or issued on the stream call by call (TD_OPT_HOST_GRAPH = 0, pageable host memory).
-struct HostCopy { void *dst; const void *src; size_t bytes; };
 
 static void host_chunk_copies(const td_handle *h, const td_step_io *io, const td_host_io *host, size_t b, size_t n,
                               std::vector<HostCopy> &in, std::vector<HostCopy> &out)
@@ -817,9 +825,10 @@ static void host_chunk_copies(const td_handle *h, const td_step_io *io, const td
     const size_t atk_w = TD_ROADS * TD_CLUSTER;
     in.clear();
     out.clear();
-    if (h->kind != TD_KIND_ATK)
+    // (a NULL host pointer here: the kernel reads that input straight from the caller's page-locked buffer, td_step_host)
+    if (h->kind != TD_KIND_ATK && host->def_action_host)
         in.push_back({(int64_t *)io->def_action_dev + b * def_w, host->def_action_host + b * def_w, n * def_w * 8});
-    if (h->kind != TD_KIND_DEF)
+    if (h->kind != TD_KIND_DEF && host->atk_action_host)
         in.push_back({(int64_t *)io->atk_action_dev + b * atk_w, host->atk_action_host + b * atk_w, n * atk_w * 8});
     if (h->kind == TD_KIND_ATK && io->def_action_dev && host->def_action_host)       // host-resolved scripted defender
         in.push_back({(int64_t *)io->def_action_dev + b, host->def_action_host + b, n * 8});
@@ -868,37 +877,78 @@ static bool host_pointer_is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
 }
 
-static int host_chunk_count(const td_handle *h, const td_host_io *host)
+// How td_step_host cuts the batch.  Measured on B200 (tools/e2e_sweep.py, profiles/r02_e2e_sweep.txt; def-small, 65,536
+// envs, device step 0.2135 ms): one chunk 0.2462 ms per call; CHAINED chunk kernels lose (every boundary costs ~10 us:
+// 2 / 4 chunks 0.2512 / 0.2790 ms); INDEPENDENT chunk kernels -- graph branches that start as soon as their own
+// actions are in, and fill the SMs the chunk before them leaves -- win when the first chunk is short: chunks of
+// n/16, 3n/16, 9n/16, rest = 0.2380 ms (0.90 of the device step; 2p-large 0.5424 -> 0.4806 ms, def-middle 0.4489 ->
+// 0.4387 ms).  When the action copy is as long as the step (>= 8 MB: the attacker's (3, 8) int64 action at 65,536 envs,
+// Box actions) equal chunks are better (atk-small 0.5760 -> 0.4530 ms, PCIe-bound).
+struct HostPlan { int chunks; int first; bool chain; };
+
+static HostPlan host_plan(const td_handle *h, const td_step_io *io, const td_host_io *host, bool graph)
 {
-    // measured on B200 (def-small, 65,536 envs, tools/e2e_sweep.py): every extra chained chunk costs ~10 us of kernel
-    // boundary, more than the copy time it hides (1 / 2 / 4 chunks: 0.290 / 0.301 / 0.326 ms per step before the
-    // outputs became zero-copy, 0.242 / 0.252 / 0.269 after), so one chunk is the default
-    (void)host;
-    const int chunks = h->host_chunks > 0 ? h->host_chunks : 1;
-    return std::max(1, std::min(chunks, h->n_envs));
+    HostPlan p;
+    const size_t cells = (size_t)h->cells;
+    // bytes per env that travel through copy nodes (inputs the kernel reads from host memory itself do not count)
+    const size_t action_bytes = ((h->kind != TD_KIND_ATK && host->def_action_host) ? (io->multi_action ? 6 * cells * 8 : 8) : 0) +
+                                ((h->kind != TD_KIND_DEF && host->atk_action_host) ? (size_t)TD_ROADS * TD_CLUSTER * 8 : 0);
+    const bool automatic = h->host_chunks <= 0;
+    p.chain = graph ? h->host_chain : true;                       // plain stream launches are ordered by the stream
+    p.chunks = automatic ? ((graph && !p.chain && h->n_envs >= 8192 && action_bytes > 0) ? 4 : 1) : h->host_chunks;
+    p.chunks = std::max(1, std::min(p.chunks, h->n_envs));
+    // a copy about as long as the step (>= 8 MB) wants equal chunks, a short one a short first chunk
+    p.first = h->host_first_chunk >= 0 ? h->host_first_chunk
+                                       : ((automatic && action_bytes * (size_t)h->n_envs < ((size_t)8 << 20)) ? h->n_envs / 16 : 0);
+    return p;
 }
 
-static int build_host_graph(td_handle *h, const td_step_io *io, const td_host_io *host, int chunks, bool incremental,
+// envs per chunk: equal parts, or -- first = F > 0 -- chunks that grow by a factor of three (F, 3F, 9F, ..., the last
+// one takes the rest): the first actions arrive after a few microseconds and every kernel finds its inputs in place
+// when the one before it drains
+static std::vector<int> host_chunk_sizes(const td_handle *h, const HostPlan &plan)
+{
+    std::vector<int> counts;
+    int left = h->n_envs;
+    if (plan.first > 0 && plan.chunks >= 2) {
+        long long size = plan.first;
+        while ((int)counts.size() < plan.chunks - 1 && size < left) {
+            counts.push_back((int)size);
+            left -= (int)size;
+            size *= 3;
+        }
+        counts.push_back(left);
+        return counts;
+    }
+    const int parts = std::max(1, std::min(plan.chunks, left));
+    for (int c = 0; c < parts; ++c) counts.push_back(left / parts + (c < left % parts ? 1 : 0));
+    return counts;
+}
+
+static int build_host_graph(td_handle *h, const td_step_io *io, const td_host_io *host, const HostPlan &plan, bool incremental,
                             cudaGraphExec_t *exec_out)
 {
     cudaGraph_t g = nullptr;
     TD_CUDA(h, cudaGraphCreate(&g, 0));
     auto bail = [&](int rc) { cudaGraphDestroy(g); return rc; };
-    const int base = h->n_envs / chunks, rem = h->n_envs % chunks;
     std::vector<HostCopy> in, out;
     cudaGraphNode_t prev_kernel = nullptr;
+    std::vector<cudaGraphNode_t> prev_copies;
     int begin = 0;
-    for (int c = 0; c < chunks; ++c) {
-        const int count = base + (c < rem ? 1 : 0);
+    for (int count : host_chunk_sizes(h, plan)) {
         host_chunk_copies(h, io, host, (size_t)begin, (size_t)count, in, out);
         std::vector<cudaGraphNode_t> deps;
         for (const HostCopy &cp : in) {
+            // input copies of successive chunks follow each other (chunk order on the copy engine); the kernels are
+            // chained too, or -- host_chain off -- independent branches that start as soon as their own inputs are in
             cudaGraphNode_t n;
-            cudaError_t e = cudaGraphAddMemcpyNode1D(&n, g, nullptr, 0, cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice);
+            cudaError_t e = cudaGraphAddMemcpyNode1D(&n, g, plan.chain ? nullptr : prev_copies.data(), plan.chain ? 0 : prev_copies.size(),
+                                                     cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice);
             if (e != cudaSuccess) return bail(fail(h, TD_E_CUDA, std::string("td_step_host: memcpy node: ") + cudaGetErrorString(e)));
             deps.push_back(n);
         }
-        if (prev_kernel) deps.push_back(prev_kernel);
+        prev_copies = deps;
+        if (prev_kernel && plan.chain) deps.push_back(prev_kernel);
         LaunchTarget t;
         t.graph = g;
         t.deps = deps.data();
@@ -929,7 +979,8 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
     if (h->kind != TD_KIND_DEF && !host->atk_action_host) return fail(h, TD_E_INVALID, "td_step_host: atk_action_host is required");
     TD_CUDA(h, cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
-    td_step_io io_packed;
+    td_step_io io_local = *io;
+    td_host_io host_local = *host;
     if (host->packed_host) {
         // zero-copy outputs: the kernel stores every env's packed record straight into the caller's page-locked buffer
         void *dptr = nullptr;
@@ -937,24 +988,71 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
             cudaGetLastError();
             return fail(h, TD_E_INVALID, "td_step_host: packed_host must be page-locked, device-mapped host memory");
         }
-        io_packed = *io;
-        io_packed.packed_out_dev = dptr;
-        io = &io_packed;
+        io_local.packed_out_dev = dptr;
     }
+    {
+        // zero-copy inputs: the step kernel reads small actions from the caller's page-locked buffer itself.  For the
+        // 8-byte Discrete action that costs +1.2 us per step at 65,536 envs against +13 us for a copy-engine node in
+        // front of the kernel (tools/e2e_breakdown.py: def-small 0.2376 -> 0.2317 ms per call).  Kernel-side PCIe reads
+        // sustain ~20 GB/s, so the rule is bytes per env against the env's share of the step (~ its observation):
+        // 3 x action bytes <= cells.  That takes the (3, 8) int64 attacker action on 30x30 boards (2p-large 0.4868 ->
+        // 0.4702 ms) and leaves it to the copy engine on 10x10 boards (atk-small: 0.4551 ms copied, 0.6117 ms zero-copy).
+        auto mapped = [](const void *hp) -> void * {
+            void *d = nullptr;
+            if (!hp || cudaHostGetDevicePointer(&d, const_cast<void *>(hp), 0) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+            return d;
+        };
+        const int zc = h->host_zero_copy;
+        const size_t def_bytes = io->multi_action ? 6 * (size_t)h->cells * 8 : 8, atk_bytes = (size_t)TD_ROADS * TD_CLUSTER * 8;
+        auto wanted = [&](size_t bytes_per_env) { return zc > 0 || (zc < 0 && 3 * bytes_per_env <= (size_t)h->cells); };
+        if (h->kind != TD_KIND_ATK && wanted(def_bytes))
+            if (void *d = mapped(host->def_action_host)) { io_local.def_action_dev = static_cast<const int64_t *>(d); host_local.def_action_host = nullptr; }
+        if (h->kind != TD_KIND_DEF && wanted(atk_bytes))
+            if (void *d = mapped(host->atk_action_host)) { io_local.atk_action_dev = static_cast<const int64_t *>(d); host_local.atk_action_host = nullptr; }
+    }
+    io = &io_local;
+    host = &host_local;
     const bool incremental = obs_is_current(h, io);
-    const int chunks = host_chunk_count(h, host);
     h->obs_synced = nullptr;                                    // until every chunk was launched
 
     // the PCIe-bound variant that also ships the observation (1.2 GB per step at 65,536 envs) gains nothing from a
     // graph and measured slower through graph memcpy nodes (1.9e6 vs 3.1e6 env-steps/s): plain stream copies
     bool use_graph = h->host_graph != 0 && host->obs_host == nullptr;
+    {
+        // nothing left to copy in either direction: the call is one kernel launch and the synchronisation
+        std::vector<HostCopy> &in = h->host_in, &out = h->host_out;
+        host_chunk_copies(h, io, host, 0, (size_t)h->n_envs, in, out);
+        if (in.empty() && out.empty()) use_graph = false;
+    }
+    td_handle::HostGraph *hit = nullptr;
+    std::vector<unsigned char> &key = h->host_key;              // scratch of the handle: no allocation per call
+    HostPlan plan = {1, 0, true};
     if (use_graph) {
-        // a graph keeps raw host addresses: only page-locked buffers qualify
-        const void *hp[] = {host->def_action_host, host->atk_action_host, host->opponent_host, host->obs_host,
-                            host->reward_host, host->done_host, host->win_host, host->allow_next_host,
-                            host->real_def_host, host->real_atk_host, host->fail_def_host, host->fail_atk_host,
-                            host->opponent_cluster_host, host->packed_host};
-        for (const void *p : hp) use_graph = use_graph && host_pointer_is_pinned(p);
+        // everything a graph bakes in: the buffers of both structs, the cut of the batch, the kernel that was picked,
+        // map pool, generators, difficulty
+        plan = host_plan(h, io, host, true);
+        const unsigned long long extra[3] = {(unsigned long long)plan.chunks | ((unsigned long long)plan.first << 20) | (plan.chain ? 1ull << 52 : 0ull),
+                                             incremental ? 1ull : 0ull, h->cfg_generation};
+        const void *ptrs[3] = {h->maps, h->mt, h->records};
+        const int ints[2] = {h->difficulty | (h->opponent_seeded ? 0x100 : 0) | (h->map_stride << 9), h->n_maps};
+        key.resize(sizeof(td_step_io) + sizeof(td_host_io) + sizeof(extra) + sizeof(ints) + sizeof(ptrs));
+        unsigned char *k = key.data();
+        memcpy(k, io, sizeof(td_step_io)); k += sizeof(td_step_io);
+        memcpy(k, host, sizeof(td_host_io)); k += sizeof(td_host_io);
+        memcpy(k, extra, sizeof(extra)); k += sizeof(extra);
+        memcpy(k, ints, sizeof(ints)); k += sizeof(ints);
+        memcpy(k, ptrs, sizeof(ptrs));
+        for (auto &g : h->host_graphs)
+            if (g.key == key) { hit = &g; break; }
+        if (!hit) {
+            // a graph keeps raw host addresses: only page-locked buffers qualify (checked when the graph is built;
+            // a cached graph vouches for its buffers as long as the caller keeps them allocated)
+            const void *hp[] = {host->def_action_host, host->atk_action_host, host->opponent_host, host->obs_host,
+                                host->reward_host, host->done_host, host->win_host, host->allow_next_host,
+                                host->real_def_host, host->real_atk_host, host->fail_def_host, host->fail_atk_host,
+                                host->opponent_cluster_host, host->packed_host};
+            for (const void *q : hp) use_graph = use_graph && host_pointer_is_pinned(q);
+        }
     }
     if (use_graph) {
         if (s == nullptr || s == cudaStreamLegacy) {
@@ -963,26 +1061,9 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
             if (!h->host_stream) TD_CUDA(h, cudaStreamCreateWithFlags(&h->host_stream, cudaStreamDefault));
             s = h->host_stream;
         }
-        std::vector<unsigned char> key(sizeof(td_step_io) + sizeof(td_host_io) + 3 * sizeof(unsigned long long));
-        unsigned long long extra[3] = {(unsigned long long)chunks, incremental ? 1ull : 0ull, h->cfg_generation};
-        memcpy(key.data(), io, sizeof(td_step_io));
-        memcpy(key.data() + sizeof(td_step_io), host, sizeof(td_host_io));
-        memcpy(key.data() + sizeof(td_step_io) + sizeof(td_host_io), extra, sizeof(extra));
-        std::vector<unsigned char> state(2 * sizeof(int) + sizeof(void *) * 3);
-        // everything else a kernel node bakes in: map pool, generators, difficulty
-        {
-            const void *ptrs[3] = {h->maps, h->mt, h->records};
-            int ints[2] = {h->difficulty | (h->opponent_seeded ? 0x100 : 0) | (h->map_stride << 9), h->n_maps};
-            memcpy(state.data(), ints, sizeof(ints));
-            memcpy(state.data() + sizeof(ints), ptrs, sizeof(ptrs));
-        }
-        key.insert(key.end(), state.begin(), state.end());
-        td_handle::HostGraph *hit = nullptr;
-        for (auto &g : h->host_graphs)
-            if (g.key == key) { hit = &g; break; }
         if (!hit) {
             cudaGraphExec_t exec = nullptr;
-            rc = build_host_graph(h, io, host, chunks, incremental, &exec);
+            rc = build_host_graph(h, io, host, plan, incremental, &exec);
             if (rc != TD_OK) return rc;
             if (h->host_graphs.size() >= 16) {                      // evict the least recently used
                 size_t lru = 0;
@@ -998,11 +1079,9 @@ extern "C" int td_step_host(td_handle *h, const td_step_io *io, const td_host_io
         TD_CUDA(h, cudaGraphLaunch(hit->exec, s));
     } else {
         // plain stream launches, chunk by chunk (pageable host memory or TD_OPT_HOST_GRAPH = 0)
-        const int base = h->n_envs / chunks, rem = h->n_envs % chunks;
-        std::vector<HostCopy> in, out;
+        std::vector<HostCopy> &in = h->host_in, &out = h->host_out;
         int begin = 0;
-        for (int c = 0; c < chunks; ++c) {
-            const int count = base + (c < rem ? 1 : 0);
+        for (int count : host_chunk_sizes(h, host_plan(h, io, host, false))) {
             host_chunk_copies(h, io, host, (size_t)begin, (size_t)count, in, out);
             for (const HostCopy &cp : in) TD_CUDA(h, cudaMemcpyAsync(cp.dst, cp.src, cp.bytes, cudaMemcpyHostToDevice, s));
             LaunchTarget t;
@@ -1042,6 +1121,21 @@ extern "C" int td_set_option(td_handle *h, int option, int value)
     case TD_OPT_OBS_SMEM_KB:
         if (value < 0 || value > 227) return fail(h, TD_E_INVALID, "td_set_option: shared memory out of range");
         h->obs_smem_kb = value;
+        return TD_OK;
+    case TD_OPT_HOST_CHAIN:
+        h->host_chain = value != 0;
+        h->cfg_generation += 1;      // cached host-step graphs were built with the other shape
+        return TD_OK;
+    case TD_OPT_HOST_FIRST_CHUNK:
+        h->host_first_chunk = value < 0 ? -1 : value;
+        h->cfg_generation += 1;
+        return TD_OK;
+    case TD_OPT_HOST_ZERO_COPY:
+        h->host_zero_copy = value < 0 ? -1 : value > 0 ? 1 : 0;
+        return TD_OK;
+    case TD_OPT_GENERIC_KERNELS:
+        h->generic_kernels = value != 0;
+        h->cfg_generation += 1;      // cached host-step graphs hold the kernel that was picked when they were built
         return TD_OK;
     default: return fail(h, TD_E_INVALID, "td_set_option: unknown option");
     }

@@ -303,15 +303,28 @@ typedef struct td_host_io {
                                         td_step_host issues no device->host copy at all. */
 } td_host_io;
 int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, void *stream);
-/* td_step_host runs as ONE CUDA-graph launch per call (copies in, the step kernels of 1..n chained chunks of the
- * batch, copies out), cached per distinct set of buffers; with pageable host memory, or TD_OPT_HOST_GRAPH = 0, the
- * same operations are issued on the stream one by one.  Passing the legacy default stream (NULL) is fine. */
+/* td_step_host runs as ONE CUDA-graph launch per call (copies in, the step kernels of 1..n chunks of the batch,
+ * copies out), cached per distinct set of buffers; with pageable host memory, or TD_OPT_HOST_GRAPH = 0, the same
+ * operations are issued on the stream one by one.  Large batches are cut automatically: the chunk kernels are
+ * independent branches of the graph, each starts as soon as its own actions have arrived (the first chunk is short),
+ * so the action copy hides behind the step.  Buffers of a cached graph must stay allocated (and page-locked) while
+ * the handle lives.  Passing the legacy default stream (NULL) is fine. */
 
 /* tuning knobs of a handle (no environment variables are read anywhere in the library) */
-enum { TD_OPT_HOST_CHUNKS = 1,   /* td_step_host: chunks the batch is cut into; 0 = automatic */
+enum { TD_OPT_HOST_CHUNKS = 1,   /* td_step_host: chunks the batch is cut into; 0 = automatic (4 from 8,192 envs on) */
        TD_OPT_HOST_GRAPH = 2,    /* td_step_host: 1 = graph launch (default), 0 = plain stream launches */
        TD_OPT_STEP_SMEM_KB = 3,  /* experiments: minimum dynamic shared memory of a step CTA (lowers residency) */
-       TD_OPT_OBS_SMEM_KB = 4 }; /* experiments: the same for td_observe */
+       TD_OPT_OBS_SMEM_KB = 4,   /* experiments: the same for td_observe */
+       TD_OPT_GENERIC_KERNELS = 5, /* 1 = never pick the step kernels specialised on the default scripted opponent
+                                    (level 1 on the device generator); results are identical, for A/B runs and tests */
+       TD_OPT_HOST_CHAIN = 6,    /* td_step_host graph with > 1 chunk: 0 = independent branches, each starts when its own
+                                    actions have arrived (default), 1 = chunk kernels run one after the other */
+       TD_OPT_HOST_FIRST_CHUNK = 7 }; /* td_step_host with > 1 chunk: F > 0 = chunks of F, 3F, 9F, ... envs (the last takes the
+                                    rest), 0 = equal chunks, -1 = automatic (n/16 unless the copy is >= 8 MB) */
+enum { TD_OPT_HOST_ZERO_COPY = 8 }; /* td_step_host inputs the step kernel reads straight from the caller's page-locked
+                                    buffer instead of a copy in front of it: -1 = automatic (3 x action bytes per env <=
+                                    cells: Discrete actions always, the (3, 8) attacker action on 30x30 boards),
+                                    0 = never, 1 = every action */
 int td_set_option(td_handle *h, int option, int value);
 
 /* raw env records (td_layout) to/from host; blob is n * record_bytes */

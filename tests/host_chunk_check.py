@@ -1,4 +1,5 @@
-"""Subprocess body of test_gpu_env.py::test_chunked_host_path_equals_device_path: argv = chunks, graph (0/1)."""
+"""Subprocess body of test_gpu_env.py::test_chunked_host_path_equals_device_path: argv = chunks, graph (0/1)
+[, chain (0/1), envs in the first chunk (-1 = automatic), zero-copy inputs (-1 automatic / 0 / 1)]."""
 import os
 import sys
 
@@ -15,6 +16,12 @@ def main():
         b.reset()
         b.engine.set_option("host_chunks", int(sys.argv[1]))
         b.engine.set_option("host_graph", int(sys.argv[2]))
+        if len(sys.argv) > 3:
+            b.engine.set_option("host_chain", int(sys.argv[3]))
+        if len(sys.argv) > 4:
+            b.engine.set_option("host_first_chunk", int(sys.argv[4]))
+        if len(sys.argv) > 5:
+            b.engine.set_option("host_zero_copy", int(sys.argv[5]))
         g = torch.Generator(device="cuda").manual_seed(1)
         for t in range(60):
             d = torch.randint(0, 6 * L * L + 1, (N,), device="cuda", generator=g)

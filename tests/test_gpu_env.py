@@ -516,14 +516,18 @@ def test_checkpoint_resume_is_bit_identical(kind):
     env.close()
 
 
-@pytest.mark.parametrize("chunks,graph", [("1", "1"), ("3", "1"), ("4", "1"), ("0", "1"), ("3", "0")])
-def test_chunked_host_path_equals_device_path(chunks, graph):
-    """td_step_host cuts the batch into chained chunks inside one CUDA graph (or plain stream launches); results must
-    not depend on the chunking, on the launch mode, or on which cached graph serves a call."""
+@pytest.mark.parametrize("chunks,graph,extra", [("1", "1", []), ("3", "1", []), ("4", "1", ["1"]), ("0", "1", []), ("3", "0", []),
+                                                ("4", "1", ["0", "16"]), ("3", "1", ["1", "100"]),
+                                                ("3", "1", ["0", "-1", "0"]), ("0", "1", ["0", "-1", "1"]), ("2", "0", ["0", "-1", "1"])])
+def test_chunked_host_path_equals_device_path(chunks, graph, extra):
+    """td_step_host cuts the batch into chunks inside one CUDA graph -- independent branches (default) or chained
+    kernels, equal chunks or a short first chunk followed by growing ones -- or issues plain stream launches; small
+    actions are read by the kernel straight from the page-locked host buffer (zero-copy: automatic / never / every
+    action).  Results must not depend on any of it, nor on which cached graph serves a call."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_chunk_check.py"), chunks, graph],
+    out = subprocess.run([sys.executable, os.path.join(root, "tests", "host_chunk_check.py"), chunks, graph] + extra,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-1500:]
     assert "chunked host path ok" in out.stdout

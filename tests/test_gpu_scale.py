@@ -139,3 +139,34 @@ def test_two_handles_with_different_configs_coexist():
         differ = differ or not torch.equal(ea.reward, eb.reward)
     assert differ
     ea.close(), eb.close()
+
+
+@pytest.mark.parametrize("kind,multi", [("def", False), ("def", True), ("atk", False)])
+def test_opponent_specialised_kernels_match_the_generic_ones(kind, multi):
+    """The step kernels compiled for the default scripted opponent (level 1 on the device generator, variants 5-7 of
+    td_engine.cu) and the generic ones (TD_OPT_GENERIC_KERNELS) are the same step: outputs, observation and the whole
+    env record, every step, across auto-resets; full writes and in-place observation updates."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    n, L = 96, 10
+    kw = dict(seed=77, auto_reset=True, multi_action=multi) if kind == "def" else dict(seed=77, auto_reset=True)
+    for inc in (False, True):
+        a_env = TDVecEnv(kind, L, n, incremental_obs=inc, **kw)
+        b_env = TDVecEnv(kind, L, n, incremental_obs=inc, **kw)
+        b_env.engine.set_option("generic_kernels", 1)
+        a_env.reset(), b_env.reset()
+        g = torch.Generator(device="cuda").manual_seed(5)
+        for k in range(150 if multi else 400):
+            if kind == "atk":
+                act = torch.randint(0, 5, (n, 3, 8), dtype=torch.int64, device="cuda", generator=g)
+            elif multi:
+                act = (torch.rand((n, 6, L, L), device="cuda", generator=g) < 0.02).to(torch.int64)
+            else:
+                act = torch.randint(0, 6 * L * L + 1, (n,), dtype=torch.int64, device="cuda", generator=g)
+            _, ra, da, _ = a_env.step(act)
+            _, rb, db, _ = b_env.step(act)
+            assert torch.equal(a_env.obs, b_env.obs), (kind, multi, inc, k)
+            assert torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(a_env._slab, b_env._slab), (kind, multi, inc, k)
+        torch.cuda.synchronize()
+        assert (a_env.engine.get_state_raw() == b_env.engine.get_state_raw()).all()
+        a_env.close(), b_env.close()

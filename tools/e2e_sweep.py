@@ -35,18 +35,35 @@ e.record()
 torch.cuda.synchronize()
 dev_ms = s.elapsed_time(e) / 100
 print("%s device step %.4f ms = %.3e env-steps/s" % (name, dev_ms, n / dev_ms * 1e3))
-for graph in (1, 0):
-    for chunks in (1, 2, 3, 4, 6, 8):
-        env.engine.set_option("host_graph", graph)
-        env.engine.set_option("host_chunks", chunks)
-        for k in range(8):
+def measure(tag):
+    for k in range(8):
+        env.step_host(haction(k))
+    best = 1e9
+    for r in range(3):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for k in range(60):
             env.step_host(haction(k))
-        best = 1e9
-        for r in range(3):
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            for k in range(60):
-                env.step_host(haction(k))
-            best = min(best, (time.perf_counter() - t0) / 60)
-        print("graph=%d chunks=%d: %.4f ms/step  %.3e env-steps/s  (%.2f of device)" % (graph, chunks, best * 1e3, n / best, dev_ms / (best * 1e3)))
+        best = min(best, (time.perf_counter() - t0) / 60)
+    print("%s: %.4f ms/step  %.3e env-steps/s  (%.2f of device)" % (tag, best * 1e3, n / best, dev_ms / (best * 1e3)))
+
+
+quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
+if not quick:
+    for graph in (1, 0):
+        for chunks in (1, 2, 4):
+            env.engine.set_option("host_graph", graph)
+            env.engine.set_option("host_chunks", chunks)
+            measure("graph=%d chunks=%d" % (graph, chunks))
+# independent chunk kernels (each starts when its own actions are in); first > 0: chunks of first, 3 first, 9 first, ...
+env.engine.set_option("host_graph", 1)
+for chain in ((1, 0) if quick else (0,)):
+    env.engine.set_option("host_chain", chain)
+    for chunks in ((1, 2, 3, 4, 8, 16) if quick else (2, 3, 4, 5, 6, 8)):
+        for first in ((0, n // 32, n // 16, n // 8) if quick else (0, 512, 1024, 2048, 4096, 8192)):
+            if chunks == 1 and first:
+                continue
+            env.engine.set_option("host_chunks", chunks)
+            env.engine.set_option("host_first_chunk", first)
+            measure("graph=1 %s chunks=%d first=%d" % ("chained" if chain else "unchained", chunks, first))
 env.close()
