@@ -49,6 +49,8 @@ def measure(tag):
 
 
 quick = len(sys.argv) > 2 and sys.argv[2] == "quick"
+measure("default (automatic: zero-copy inputs where they pay, independent chunks for copied inputs)")
+env.engine.set_option("host_zero_copy", 0)      # the sweeps below are about the copy path
 if not quick:
     for graph in (1, 0):
         for chunks in (1, 2, 4):
