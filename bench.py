@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--replay", type=int, default=64, help="envs per rank replayed through the CPU oracle after timing (0 = off)")
     ap.add_argument("--replay-steps", type=int, default=100)
     ap.add_argument("--no-side-workloads", action="store_true", help="skip BASELINE configs 3-5 (atk-small, def-middle-multi, 2p-large)")
+    ap.add_argument("--obs-memory", default="auto", choices=["auto", "compressible", "plain"],
+                    help="memory of the observation tensor (TDVecEnv obs_memory): compressible allocation or ordinary torch memory")
     ap.add_argument("--side-workloads-multi", action="store_true", help="run the side workloads under torchrun too")
     return ap.parse_args()
 
@@ -332,7 +334,7 @@ def side_workload(torch, dist, args, name, rank, world, local, dev):
     from gym_td_b200.vec_env import TDVecEnv
     env_id, kind, L, n_envs, multi, bpe = WORKLOADS[name]
     env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
-                   env_offset=D.rank_env_offset(rank), multi_action=multi)
+                   env_offset=D.rank_env_offset(rank), multi_action=multi, obs_memory=args.obs_memory)
     env.reset()
     action, _, _ = make_actions(torch, name, kind, L, n_envs, multi, dev, 1234 + rank)
     for k in range(args.preroll + args.warmup):
@@ -343,7 +345,7 @@ def side_workload(torch, dist, args, name, rank, world, local, dev):
     out = {"env_id": env_id, "envs_per_gpu": n_envs, "value": n_envs * max(world, 1) / (m * 1e-3), "unit": UNIT,
            "ms_per_step": m, "steps": steps, "timed_repeats": len(ms),
            "repeat_ms_per_step": [x / steps for x in ms],
-           "roofline": roofline_of(name, kind, n_envs, bpe, m)}
+           "roofline": roofline_of(name, kind, n_envs, bpe, m), "obs_memory": env.obs_memory}
     if args.replay > 0:
         out["replay"] = replay_check(torch, dist, env, action, min(args.replay, 32), min(args.replay_steps, 60),
                                      world, dev)
@@ -381,7 +383,7 @@ def main():
     env_id, kind, L, n_envs, multi, bytes_per_env_step = WORKLOADS[args.workload]
     n_envs = args.envs or n_envs
     env = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
-                   env_offset=D.rank_env_offset(rank), multi_action=multi)
+                   env_offset=D.rank_env_offset(rank), multi_action=multi, obs_memory=args.obs_memory)
     env.reset()
     action, def_pool, atk_pool = make_actions(torch, args.workload, kind, L, n_envs, multi, dev, 1234 + rank)
 
@@ -412,26 +414,33 @@ def main():
     stats = env.allreduce_stats()          # NCCL: the only collective of the path
     value = n_envs * n_gpus * args.steps / (ms * 1e-3)
 
-    # Opt-in variant (td_step_io.obs_incremental, SURVEY 8 f4): the same float32 tensor, updated in place instead
-    # of rewritten.  Reported next to the headline, never as the headline: `value` always writes all 45 planes.
-    inc = None
-    if rank == 0 and world == 1:
-        env.incremental_obs = True
+    # The observation tensor normally lives in a compressible allocation (TDVecEnv obs_memory, td_alloc_compressible):
+    # the same kernel, the same values, fewer HBM bytes on the way out.  The same step into an ordinary torch tensor
+    # is timed next to it so that the line carries both.
+    obs_mem = {"headline": env.obs_memory}
+    if rank == 0 and world == 1 and env.obs_memory == "compressible":
+        keep = env.obs
+        env.obs = torch.empty_like(keep)
         for k in range(args.warmup):
             env.step(action(k))
         torch.cuda.synchronize()
-        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s2.record()
+        s1, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s1.record()
         for k in range(args.steps):
             env.step(action(k))
-        e2.record()
+        e1.record()
         torch.cuda.synchronize()
-        ms2 = s2.elapsed_time(e2)
-        env.incremental_obs = False
+        ms1 = s1.elapsed_time(e1) / args.steps
+        env.obs = keep
         env.step(action(0))
-        inc = {"value": n_envs * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
-               "note": "observation updated in place (changed planes + old/new tower and enemy cells); "
-                       "bit-identical tensor, fewer bytes written; not comparable to the algorithmic-bytes roofline"}
+        obs_mem["plain"] = {"ms_per_step": ms1, "value": n_envs / (ms1 * 1e-3), "unit": UNIT,
+                            "roofline_frac": roofline_of(args.workload, kind, n_envs, bytes_per_env_step, ms1)["frac"],
+                            "note": "the same step writing into an ordinary (cudaMalloc / torch) tensor"}
+        obs_mem["note"] = ("headline: observation tensor in a compressible allocation (cuMemCreate, "
+                           "CU_MEM_ALLOCATION_COMP_GENERIC): lossless L2 compression on the way to HBM, transparent to "
+                           "readers; DRAM traffic falls below the algorithmic bytes")
+
+    inc = None          # measured on a fresh env further down
 
     # end to end through the host-buffer API: pinned host actions in, reward/done/info out, every step
     e2e = None
@@ -491,6 +500,31 @@ def main():
     del env
     torch.cuda.empty_cache()
 
+    # Opt-in variant (td_step_io.obs_incremental, SURVEY 8 f4): the same float32 tensor, updated in place instead
+    # of rewritten.  Reported next to the headline, never as the headline: `value` always writes all 45 planes.
+    # A fresh env, as a user would create it (TDVecEnv picks the observation memory for the mode).
+    if rank == 0 and world == 1:
+        e1 = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
+                      env_offset=D.rank_env_offset(rank), multi_action=multi, incremental_obs=True, obs_memory=args.obs_memory)
+        e1.reset()
+        for k in range(min(args.preroll, 400) + args.warmup):
+            e1.step(action(k))
+        torch.cuda.synchronize()
+        s2, e2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s2.record()
+        for k in range(args.steps):
+            e1.step(action(k))
+        e2.record()
+        torch.cuda.synchronize()
+        ms2 = s2.elapsed_time(e2)
+        inc = {"value": n_envs * args.steps / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2 / args.steps,
+               "obs_memory": e1.obs_memory,
+               "note": "observation updated in place (changed planes + old/new tower and enemy cells); "
+                       "bit-identical tensor, fewer bytes written; not comparable to the algorithmic-bytes roofline"}
+        e1.close()
+        del e1
+        torch.cuda.empty_cache()
+
     # Opt-in reduced-precision observation planes (td_step_io.obs_format): same layout, bf16 / u8
     # elements.  Reported next to the headline like the in-place update; never the headline.
     reduced = None
@@ -498,7 +532,7 @@ def main():
         reduced = {}
         for fmt in ("bf16", "u8"):
             e2 = TDVecEnv(kind, L, n_envs, seed=args.seed, device=local, difficulty=1, auto_reset=True,
-                          env_offset=D.rank_env_offset(rank), obs_format=fmt)
+                          env_offset=D.rank_env_offset(rank), obs_format=fmt, obs_memory=args.obs_memory)
             e2.reset()
             for k in range(min(args.preroll, 400) + args.warmup):
                 e2.step(action(k))
@@ -538,6 +572,7 @@ def main():
         "dtype": "f64 state / f32 observation", "data": "synthetic",
         "config": config_of(args, n_envs),
         "preroll_steps": args.preroll,
+        "obs_memory": obs_mem,
         "timing": {"timed_repeats": len(seg_ms), "steps_per_repeat": args.steps, "statistic": "median",
                    "repeat_ms_per_step": [x / args.steps for x in seg_ms],
                    "spread": (max(seg_ms) - min(seg_ms)) / ms if ms > 0 else None},

@@ -95,7 +95,8 @@ EXPORTS = ["td_abi_version", "td_last_error", "td_default_config", "td_mapgen", 
            "td_destroy", "td_set_config", "td_get_layout", "td_upload_maps", "td_set_map_stride", "td_reset",
            "td_seed_opponent", "td_set_difficulty", "td_step", "td_observe", "td_step_host", "td_get_state",
            "td_set_state", "td_get_opponent", "td_get_stats", "td_reset_stats", "td_rollout_mask", "td_rollout_record",
-           "td_gae", "td_snapshot", "td_observe_snapshot", "td_set_option", "td_packed_stride", "td_invalidate_obs", "td_observe_as"]
+           "td_gae", "td_snapshot", "td_observe_snapshot", "td_set_option", "td_packed_stride", "td_invalidate_obs", "td_observe_as",
+           "td_alloc_compressible", "td_free_compressible"]
 
 
 def lib():
@@ -140,10 +141,38 @@ def lib():
         L.td_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.td_invalidate_obs.argtypes = [C.c_void_p]
         L.td_observe_as.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.td_alloc_compressible.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.td_free_compressible.argtypes = [C.c_void_p]
         if L.td_abi_version() != 3:
             raise ImportError("libtd_b200.so ABI version mismatch")
         _lib = L
     return _lib
+
+
+class CompressibleBuffer:
+    """Device memory from td_alloc_compressible (a compressible CUDA virtual-memory allocation, zero-filled), exposed
+    through __cuda_array_interface__ so that torch.as_tensor() wraps it without a copy; freed when the last tensor
+    over it is gone.  `compressed` tells whether the driver granted compression."""
+
+    def __init__(self, nbytes, device=0):
+        ptr, granted = C.c_void_p(), C.c_int(0)
+        rc = lib().td_alloc_compressible(int(device), int(nbytes), C.byref(ptr), C.byref(granted))
+        if rc != 0:
+            raise TdError(rc, (lib().td_last_error(None) or b"").decode())
+        self.ptr, self.nbytes, self.device, self.compressed = ptr.value, int(nbytes), int(device), bool(granted.value)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2,
+                                         "strides": None}
+
+    def tensor(self, shape, dtype):
+        """A torch tensor of `shape` / `dtype` over the buffer (keeps the buffer alive)."""
+        import torch
+        flat = torch.as_tensor(self, device="cuda:%d" % self.device)
+        return flat.view(dtype).view(shape)
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr and _lib is not None:
+            _lib.td_free_compressible(C.c_void_p(ptr))
 
 
 def config_struct(cfg=None, hyper=None):

@@ -33,6 +33,7 @@
  */
 #ifndef TD_B200_H
 #define TD_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -359,6 +360,17 @@ int td_rollout_record(td_handle *h, int which, const int64_t *action_dev, const 
 int td_gae(int horizon, int n, const float *rewards_dev, const uint8_t *dones_dev, const float *values_dev,
            const float *next_value_dev, double gamma, double lam, float *advs_dev, float *returns_dev, void *stream);
 /* td_gae takes no handle: it runs on the device that owns rewards_dev (made current for the calling thread). */
+
+/* ---- observation memory (new; no counterpart in the reference) ------------------------------------------------
+ * Device memory for the observation tensor from a COMPRESSIBLE allocation (CUDA virtual memory management,
+ * CU_MEM_ALLOCATION_COMP_GENERIC): B200 compresses lines in L2 on their way to HBM, losslessly and transparently to
+ * every reader and writer.  60 % of an observation is zeros and 27 % are planes that broadcast one scalar, so the
+ * step that writes it and the learner that reads it both move fewer HBM bytes.  The buffer
+ * is zero-filled.  *compressed_out (optional) tells whether the driver granted compression; when the device does not
+ * support it the call fails with TD_E_STATE and the caller allocates ordinary memory.  Any device pointer works as
+ * td_step_io.obs_dev -- this is an allocator, not a requirement. */
+int td_alloc_compressible(int device, size_t bytes, void **ptr_out, int *compressed_out);
+int td_free_compressible(void *ptr);
 
 #ifdef __cplusplus
 }

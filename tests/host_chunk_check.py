@@ -1,5 +1,5 @@
 """Subprocess body of test_gpu_env.py::test_chunked_host_path_equals_device_path: argv = chunks, graph (0/1)
-[, chain (0/1), envs in the first chunk (-1 = automatic), zero-copy inputs (-1 automatic / 0 / 1)]."""
+[, chain (0/1), envs in the first chunk (-1 = automatic), zero-copy inputs (-1 automatic / 0 / 1), 'pageable' = ordinary host memory for the actions]."""
 import os
 import sys
 
@@ -27,8 +27,8 @@ def main():
             d = torch.randint(0, 6 * L * L + 1, (N,), device="cuda", generator=g)
             k = torch.randint(0, 5, (N, 3, 8), device="cuda", generator=g)
             act = d if kind == "def" else k if kind == "atk" else {"Attacker": k, "Defender": d}
-            hact = (d.cpu().pin_memory() if kind == "def" else k.cpu().pin_memory() if kind == "atk"
-                    else {"Attacker": k.cpu().pin_memory(), "Defender": d.cpu().pin_memory()})
+            pin = (lambda t: t.cpu()) if "pageable" in sys.argv else (lambda t: t.cpu().pin_memory())
+            hact = pin(d) if kind == "def" else pin(k) if kind == "atk" else {"Attacker": pin(k), "Defender": pin(d)}
             obs, rew, done, info = a.step(act)
             h = b.step_host(hact, want_obs=(t % 7 == 0))
             torch.cuda.synchronize()

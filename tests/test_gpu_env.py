@@ -518,12 +518,14 @@ def test_checkpoint_resume_is_bit_identical(kind):
 
 @pytest.mark.parametrize("chunks,graph,extra", [("1", "1", []), ("3", "1", []), ("4", "1", ["1"]), ("0", "1", []), ("3", "0", []),
                                                 ("4", "1", ["0", "16"]), ("3", "1", ["1", "100"]),
-                                                ("3", "1", ["0", "-1", "0"]), ("0", "1", ["0", "-1", "1"]), ("2", "0", ["0", "-1", "1"])])
+                                                ("3", "1", ["0", "-1", "0"]), ("0", "1", ["0", "-1", "1"]), ("2", "0", ["0", "-1", "1"]),
+                                                ("0", "1", ["0", "-1", "-1", "pageable"])])
 def test_chunked_host_path_equals_device_path(chunks, graph, extra):
     """td_step_host cuts the batch into chunks inside one CUDA graph -- independent branches (default) or chained
     kernels, equal chunks or a short first chunk followed by growing ones -- or issues plain stream launches; small
     actions are read by the kernel straight from the page-locked host buffer (zero-copy: automatic / never / every
-    action).  Results must not depend on any of it, nor on which cached graph serves a call."""
+    action; ordinary pageable action buffers fall back to stream copies).  Results must not depend on any of it, nor on
+    which cached graph serves a call."""
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

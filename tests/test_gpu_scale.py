@@ -170,3 +170,70 @@ def test_opponent_specialised_kernels_match_the_generic_ones(kind, multi):
         torch.cuda.synchronize()
         assert (a_env.engine.get_state_raw() == b_env.engine.get_state_raw()).all()
         a_env.close(), b_env.close()
+
+
+@pytest.mark.parametrize("kind,L,multi,inc", [("def", 10, False, False), ("def", 10, False, True), ("def", 20, True, False),
+                                              ("2p", 30, False, True)])
+def test_compressible_observation_memory_is_transparent(kind, L, multi, inc):
+    """TDVecEnv keeps the observation (and a large RealAction slab) in a compressible allocation
+    (td_alloc_compressible).  Compression is lossless and happens in L2: every output, the observation as tensors,
+    clones and host copies see it, and the env record must equal those of an env writing into ordinary torch memory."""
+    import torch
+    from gym_td_b200.vec_env import TDVecEnv
+    n = {10: 2048, 20: 512, 30: 256}[L]
+    kw = dict(seed=11, auto_reset=True, incremental_obs=inc)
+    if kind == "def":
+        kw["multi_action"] = multi
+    a = TDVecEnv(kind, L, n, obs_memory="plain", **kw)
+    b = TDVecEnv(kind, L, n, obs_memory="compressible", **kw)
+    assert a.obs_memory == "plain" and b.obs_memory in ("compressible", "plain (compression not granted)")
+    if b.obs_memory != "compressible":
+        pytest.skip("the driver did not grant a compressible allocation")
+    assert b.slab_memory == "compressible"
+    a.reset(), b.reset()
+    assert torch.equal(a.obs, b.obs)
+    g = torch.Generator(device="cuda").manual_seed(6)
+    for k in range(120):
+        d = ((torch.rand((n, 6, L, L), device="cuda", generator=g) < 0.02).to(torch.int64) if multi
+             else torch.randint(0, 6 * L * L + 1, (n,), dtype=torch.int64, device="cuda", generator=g))
+        atk = torch.randint(0, 5, (n, 3, 8), dtype=torch.int64, device="cuda", generator=g)
+        act = d if kind == "def" else atk if kind == "atk" else {"Attacker": atk, "Defender": d}
+        if k % 9 == 4:        # the host-buffer call, with the observation copied out of the compressible buffer
+            hact = d.cpu().pin_memory() if kind == "def" else {"Attacker": atk.cpu().pin_memory(), "Defender": d.cpu().pin_memory()}
+            a.step(act)
+            h = b.step_host(hact, want_obs=True)
+            assert torch.equal(h["obs"].view(torch.int32), a.obs.cpu().view(torch.int32)), (k,)
+        else:
+            a.step(act)
+            b.step(act)
+        assert torch.equal(a.obs, b.obs) and torch.equal(a._slab, b._slab), (kind, L, multi, inc, k)
+        if k % 40 == 0:
+            assert torch.equal(b.obs.clone(), a.obs) and torch.equal(b.obs[n // 2:].cpu(), a.obs[n // 2:].cpu())
+    torch.cuda.synchronize()
+    assert (a.engine.get_state_raw() == b.engine.get_state_raw()).all()
+    a.close(), b.close()
+    del b
+    torch.cuda.empty_cache()
+
+
+def test_compressible_allocator_abi():
+    """td_alloc_compressible / td_free_compressible: zero-filled device memory, errors as return codes."""
+    import ctypes as C
+    import torch
+    from gym_td_b200 import engine as E
+    lib = E.lib()
+    ptr, granted = C.c_void_p(), C.c_int(-1)
+    assert lib.td_alloc_compressible(0, 0, C.byref(ptr), C.byref(granted)) == -1          # TD_E_INVALID
+    rc = lib.td_alloc_compressible(0, 5 << 20, C.byref(ptr), C.byref(granted))
+    if rc == -4:
+        pytest.skip("no compressible memory on this device: " + lib.td_last_error(None).decode())
+    assert rc == 0 and ptr.value and granted.value in (0, 1)
+    buf = E.CompressibleBuffer(3 << 20, 0)
+    t = buf.tensor((3 << 18,), torch.float32)
+    assert t.is_cuda and float(t.abs().sum()) == 0.0
+    t.fill_(2.0)
+    assert float(t.sum()) == 2.0 * (3 << 18)
+    del t, buf
+    assert lib.td_free_compressible(ptr) == 0
+    assert lib.td_free_compressible(ptr) == -1                                               # not ours any more
+    assert lib.td_free_compressible(None) == 0
