@@ -311,20 +311,28 @@ def load_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(name):
+def load_traffic(name, compressed=False):
+    """ncu DRAM bytes per launch of the workload's step kernel (profiles/traffic.json), by observation memory."""
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return tr.get(name, {}).get("dram_bytes_per_launch")
+        return tr.get(name, {}).get("compressible" if compressed else "plain", {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
 
-def roofline_of(name, kind, n_envs, bytes_per_env_step, kernel_ms):
+def roofline_of(name, kind, n_envs, bytes_per_env_step, kernel_ms, obs_memory="plain"):
     peak, src = load_peak()
     achieved = bytes_per_env_step * n_envs / (kernel_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": load_traffic(name), "peak_source": src, "kernel": "td_step_kernel<%s>" % kind,
-            "algorithmic_bytes_per_launch": bytes_per_env_step * n_envs}
+    compressed = obs_memory == "compressible"
+    out = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+           "traffic": load_traffic(name, compressed), "peak_source": src, "kernel": "td_step_kernel<%s>" % kind,
+           "algorithmic_bytes_per_launch": bytes_per_env_step * n_envs}
+    if compressed:
+        out["note"] = ("the observation tensor is a compressible allocation: the kernel stores every algorithmic byte, L2 "
+                       "compresses the lines on their way to HBM, so `traffic` (ncu DRAM bytes) is below the algorithmic bytes "
+                       "and `frac` -- algorithmic bytes over time against the uncompressed copy peak -- can exceed 1; "
+                       "obs_memory.plain has the same kernel on ordinary memory")
+    return out
 
 
 def side_workload(torch, dist, args, name, rank, world, local, dev):
@@ -345,7 +353,7 @@ def side_workload(torch, dist, args, name, rank, world, local, dev):
     out = {"env_id": env_id, "envs_per_gpu": n_envs, "value": n_envs * max(world, 1) / (m * 1e-3), "unit": UNIT,
            "ms_per_step": m, "steps": steps, "timed_repeats": len(ms),
            "repeat_ms_per_step": [x / steps for x in ms],
-           "roofline": roofline_of(name, kind, n_envs, bpe, m), "obs_memory": env.obs_memory}
+           "roofline": roofline_of(name, kind, n_envs, bpe, m, env.obs_memory), "obs_memory": env.obs_memory}
     if args.replay > 0:
         out["replay"] = replay_check(torch, dist, env, action, min(args.replay, 32), min(args.replay_steps, 60),
                                      world, dev)
@@ -578,7 +586,7 @@ def main():
                    "spread": (max(seg_ms) - min(seg_ms)) / ms if ms > 0 else None},
         "gpu_launches": args.steps * len(seg_ms),
         "clocks": clk,
-        "roofline": roofline_of(args.workload, kind, n_envs, bytes_per_env_step, kernel_ms),
+        "roofline": roofline_of(args.workload, kind, n_envs, bytes_per_env_step, kernel_ms, obs_mem["headline"]),
         "episode_stats": stats,
     }
     if cores_per_rank:

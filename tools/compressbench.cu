@@ -15,7 +15,15 @@
 #define CU(x) do { CUresult r_ = (x); if (r_ != CUDA_SUCCESS) { const char *s_; cuGetErrorString(r_, &s_); printf("%s: %s\n", #x, s_); exit(1); } } while (0)
 constexpr int kN4 = 1125;      // float4 per env (45 planes x 25)
 
-// MODE 0: all zeros; 1: realistic mix; 2: realistic mix + sparse fix-ups
+// MODE 0: all zeros; 1: realistic mix; 2: realistic mix + sparse 4-byte fix-ups on top of the dense stores;
+// 3: the dense pass leaves out the float4 that hold a sparse value, those get a 16-byte zero store and then the 4-byte value;
+// 4: the dense pass leaves them out and each gets ONE 16-byte store with the value in place (every byte written once)
+__device__ __forceinline__ bool flagged(int plane, int l)
+{
+    if (plane >= 15 && plane <= 18) return l < 8;                                   // cells = lane, lanes with (lane & 3) == plane - 15
+    if (plane >= 25 && plane <= 32) { const int r = plane - 25; return l < 16 && ((2 * l) & 7) == (r & 6) ? true : false; }
+    return false;
+}
 template <int RB, int MODE>
 __global__ void __launch_bounds__(128) k(float4 *out, int4 *rec, int n)
 {
@@ -43,13 +51,30 @@ __global__ void __launch_bounds__(128) k(float4 *out, int4 *rec, int n)
                 x = plane == 9 ? make_float4(a * 0.03125f * lane, 0.f, b * 0.0625f, 0.f) : make_float4(a, 0.f, 0.f, b);
             }
         }
-        if (lane < 25) p[plane * 25 + lane] = x;
+        if (lane < 25 && !(MODE >= 3 && flagged(plane, lane))) p[plane * 25 + lane] = x;
     }
     if (MODE == 2) {
         __syncwarp();
         float *f = reinterpret_cast<float *>(p);
         f[(15 + (lane & 3)) * 100 + lane] = 1.f;
         f[(25 + (lane & 7)) * 100 + lane * 2] = 0.5f + v;
+    }
+    if (MODE == 3) {
+        float *f = reinterpret_cast<float *>(p);
+        const int i1 = (15 + (lane & 3)) * 100 + lane, i2 = (25 + (lane & 7)) * 100 + lane * 2;
+        p[i1 >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        p[i2 >> 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
+        f[i1] = 1.f;
+        f[i2] = 0.5f + v;
+    }
+    if (MODE == 4) {
+        const int i1 = (15 + (lane & 3)) * 100 + lane, i2 = (25 + (lane & 7)) * 100 + lane * 2;
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        (&a.x)[i1 & 3] = 1.f;
+        (&b.x)[i2 & 3] = 0.5f + v;
+        p[i1 >> 2] = a;
+        p[i2 >> 2] = b;
     }
     if (RB > 0 && lane < 24) r[lane] = make_int4(acc + 1, acc, 1, 1);
 }
@@ -133,6 +158,9 @@ int main()
     run("zeros, 1 KB record", k<1024, 0>, rec);
     run("realistic planes, 1 KB record", k<1024, 1>, rec);
     run("realistic planes + fix-ups, 1 KB record", k<1024, 2>, rec);
+    run("dense leaves holes, 16 B zero + 4 B value, 1 KB", k<1024, 3>, rec);
+    run("dense leaves holes, one 16 B store each, 1 KB", k<1024, 4>, rec);
+    run("dense leaves holes, one 16 B store, no record", k<0, 4>, rec);
     // fill through the runtime
     float a = timeit([&] { cudaMemsetAsync(plain, 0, bytes); }), b = timeit([&] { cudaMemsetAsync(comp, 0, bytes); });
     printf("cudaMemset of the buffer: cudaMalloc %.4f ms | compressible %.4f ms\n", a, b);

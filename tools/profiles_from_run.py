@@ -1,5 +1,5 @@
 """Turn one tools/round_measure.sh run (gpurun_out/<R>_*) into the tracked summaries under profiles/:
-    python tools/profiles_from_run.py r02f r02
+    python tools/profiles_from_run.py r02g r02 [compressible|plain]       (memory of the observation tensor in that run)
 <out>_step_<workload>_{ncu_full.txt, sass_top.txt, metrics.json}, <out>_bench_def_small.json, <out>_bench_reference_arm.json,
 <out>_launches_def_small.csv, <out>_e2e_sweep.txt and profiles/traffic.json (DRAM bytes per launch, read by bench.py)."""
 import csv
@@ -21,6 +21,7 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 def main():
     run, out = sys.argv[1], sys.argv[2]
+    memory = sys.argv[3] if len(sys.argv) > 3 else "compressible"
     G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
     traffic_path = os.path.join(P, "traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
@@ -48,8 +49,9 @@ def main():
         shutil.copy(os.path.join(G, "%s_step_%s_sass_top.txt" % (run, wl)), os.path.join(P, "%s_step_%s_sass_top.txt" % (out, wl)))
         rd = float(m["dram__bytes_read.sum"]["value"]) * SCALE[m["dram__bytes_read.sum"]["unit"]]
         wr = float(m["dram__bytes_write.sum"]["value"]) * SCALE[m["dram__bytes_write.sum"]["unit"]]
-        traffic[wl] = {"dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
-                       "source": "ncu --set full --clock-control none, one launch after 1,305 steps (profiles/%s_step_%s_metrics.json)" % (out, wl)}
+        traffic.setdefault(wl, {})[memory] = {
+            "dram_bytes_per_launch": rd + wr, "dram_bytes_read": rd, "dram_bytes_write": wr,
+            "source": "ncu --set full --clock-control none, one launch after 1,305 steps (profiles/%s_step_%s_metrics.json)" % (out, wl)}
     json.dump(traffic, open(traffic_path, "w"), indent=1)
     for src, dst in (("%s_bench.json" % run, "%s_bench_def_small.json" % out), ("%s_bench_reference.json" % run, "%s_bench_reference_arm.json" % out),
                      ("%s_launches.csv" % run, "%s_launches_def_small.csv" % out), ("%s_e2e_sweep.txt" % run, "%s_e2e_sweep.txt" % out)):
