@@ -14,6 +14,7 @@
 //   bulkzero : everything bulk-stored from the zero page (upper bound of the bulk path, no staging work)
 #include <cstdio>
 #include <cstdlib>
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); exit(1); } } while (0)
@@ -27,6 +28,30 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// `comp` on the command line: the output buffer comes from a compressible allocation (section 7.2h) instead of cudaMalloc
+static bool g_compressible = false;
+static unsigned char *alloc_out(size_t bytes)
+{
+    unsigned char *p = nullptr;
+    if (!g_compressible) { CK(cudaMalloc(&p, bytes)); return p; }
+    CUmemAllocationProp prop = {};
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = 0;
+    prop.allocFlags.compressionType = CU_MEM_ALLOCATION_COMP_GENERIC;
+    size_t gran = 0;
+    cuMemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+    const size_t size = (bytes + gran - 1) / gran * gran;
+    CUmemGenericAllocationHandle h;
+    CUdeviceptr d = 0;
+    CUmemAccessDesc acc = {};
+    acc.location = prop.location;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    if (cuMemCreate(&h, size, &prop, 0) != CUDA_SUCCESS || cuMemAddressReserve(&d, size, gran, 0, 0) != CUDA_SUCCESS ||
+        cuMemMap(d, size, 0, h, 0) != CUDA_SUCCESS || cuMemSetAccess(d, size, &acc, 1) != CUDA_SUCCESS) { printf("compressible allocation failed\n"); exit(1); }
+    return reinterpret_cast<unsigned char *>(d);
+}
 
 constexpr int kRuns = 11;
 __constant__ int kRunPlanes[kRuns] = {4, 1, 1, 3, 1, 1, 4, 6, 4, 16, 4};      // S Z S Z S Z S Z S Z S
@@ -246,7 +271,7 @@ void run(int n_envs, int ctas_per_sm_list_n, const int *ctas_per_sm_list)
 {
     size_t bytes = (size_t)n_envs * 45 * PB;
     unsigned char *out; int4 *rec;
-    CK(cudaMalloc(&out, bytes)); CK(cudaMalloc(&rec, (size_t)n_envs * 1024)); CK(cudaMemset(rec, 1, (size_t)n_envs * 1024));
+    out = alloc_out(bytes); CK(cudaMalloc(&rec, (size_t)n_envs * 1024)); CK(cudaMemset(rec, 1, (size_t)n_envs * 1024));
     const double gb = bytes / 1e9;
     const int grid = (n_envs + 3) / 4;
     const size_t need = (size_t)ZP * PB + 4 * 2 * SP * PB;
@@ -306,11 +331,15 @@ void run(int n_envs, int ctas_per_sm_list_n, const int *ctas_per_sm_list)
     }
     printf("  check: %d bad words, fix-up [15][0] = %g\n", bad, h[15 * (PB / 4)]);
     free(h);
-    cudaFree(out); cudaFree(rec);
+    if (!g_compressible) cudaFree(out);
+    cudaFree(rec);
 }
 
-int main()
+int main(int argc, char **argv)
 {
+    g_compressible = argc > 1 && argv[1][0] == 'c';
+    CK(cudaFree(0));
+    printf("output buffer: %s\n", g_compressible ? "compressible allocation" : "cudaMalloc");
     const int small[] = {6, 5, 4, 3, 2};
     run<400, 4, 16>(65536, 5, small);
     run<400, 4, 6>(65536, 5, small);
