@@ -18,6 +18,7 @@ constexpr int kN4 = 1125;      // float4 per env (45 planes x 25)
 // MODE 0: all zeros; 1: realistic mix; 2: realistic mix + sparse 4-byte fix-ups on top of the dense stores;
 // 3: the dense pass leaves out the float4 that hold a sparse value, those get a 16-byte zero store and then the 4-byte value;
 // 4: the dense pass leaves them out and each gets ONE 16-byte store with the value in place (every byte written once)
+// 5: as 2, but every fix-up follows the dense store of its own plane at once (the line cannot have left L2)
 __device__ __forceinline__ bool flagged(int plane, int l)
 {
     if (plane >= 15 && plane <= 18) return l < 8;                                   // cells = lane, lanes with (lane & 3) == plane - 15
@@ -51,7 +52,12 @@ __global__ void __launch_bounds__(128) k(float4 *out, int4 *rec, int n)
                 x = plane == 9 ? make_float4(a * 0.03125f * lane, 0.f, b * 0.0625f, 0.f) : make_float4(a, 0.f, 0.f, b);
             }
         }
-        if (lane < 25 && !(MODE >= 3 && flagged(plane, lane))) p[plane * 25 + lane] = x;
+        if (lane < 25 && !((MODE == 3 || MODE == 4) && flagged(plane, lane))) p[plane * 25 + lane] = x;
+        if (MODE == 5) {
+            float *f = reinterpret_cast<float *>(p);
+            if (plane >= 15 && plane <= 18) { __syncwarp(); if ((lane & 3) == plane - 15) f[plane * 100 + lane] = 1.f; }
+            if (plane >= 25 && plane <= 32) { __syncwarp(); if ((lane & 7) == plane - 25) f[plane * 100 + lane * 2] = 0.5f + v; }
+        }
     }
     if (MODE == 2) {
         __syncwarp();
@@ -161,6 +167,7 @@ int main()
     run("dense leaves holes, 16 B zero + 4 B value, 1 KB", k<1024, 3>, rec);
     run("dense leaves holes, one 16 B store each, 1 KB", k<1024, 4>, rec);
     run("dense leaves holes, one 16 B store, no record", k<0, 4>, rec);
+    run("fix-ups right behind their plane, 1 KB record", k<1024, 5>, rec);
     // fill through the runtime
     float a = timeit([&] { cudaMemsetAsync(plain, 0, bytes); }), b = timeit([&] { cudaMemsetAsync(comp, 0, bytes); });
     printf("cudaMemset of the buffer: cudaMalloc %.4f ms | compressible %.4f ms\n", a, b);
