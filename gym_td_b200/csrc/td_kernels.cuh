@@ -43,6 +43,11 @@ extern __shared__ __align__(16) uint8_t td_smem[];
                                  // kinds gain nothing or lose (multi-action: +5 % at 7); its in-place-observation variant is
                                  // best at 7 (0.2075 vs 0.2195 ms at 8)
 
+#ifndef TD_MIN_BLOCKS_DEF_SMALL
+#define TD_MIN_BLOCKS_DEF_SMALL 8   // 10x10 boards, Discrete defender env: 64 registers without spills, 8 CTAs per SM.  Lost while
+#endif                              // the step was HBM-bound (round 1); with the observation in compressible memory the SM side
+                                    // bounds it and 32 warps per SM win: def-small 0.1842 -> 0.1809 ms, in-place 0.1601 -> 0.1579 ms
+
 // One env's rules for one step: load the record, apply the actions / scripted opponent, advance the board, emit
 // the per-env outputs, auto-reset.  Leaves the updated record in the slice and starts the asynchronous copy of
 // the next step's generator words into the slice's word cache (the caller waits for it before store_env).
@@ -262,7 +267,9 @@ __device__ __forceinline__ void env_rules(const StepParams &p, const int env, W 
 // INC: the observation is an in-place update of the previous one (td_step_io.obs_incremental, vouched for by the
 // engine); a separate instantiation, so that the full-write kernels carry none of its code.
 template <int KIND, bool MULTI, int CELLS, int NCHUNK, int GW, bool INC, class OT = float, int OPP = -1>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, (KIND == TD_KIND_ATK && CELLS == 100) ? (INC ? 7 : TD_MIN_BLOCKS_ATK) : TD_MIN_BLOCKS) td_step_kernel(const __grid_constant__ StepParams p)
+__global__ void __launch_bounds__(kWarpsPerCta * 32, (KIND == TD_KIND_ATK && CELLS == 100) ? (INC ? 7 : TD_MIN_BLOCKS_ATK)
+                                                     : (KIND == TD_KIND_DEF && !MULTI && CELLS == 100) ? TD_MIN_BLOCKS_DEF_SMALL : TD_MIN_BLOCKS)
+td_step_kernel(const __grid_constant__ StepParams p)
 {
     // one group of GW lanes per game instance (GW = 16: two instances share a warp)
     const int group = threadIdx.x / GW;
