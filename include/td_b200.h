@@ -41,7 +41,9 @@ extern "C" {
 #endif
 
 #define TD_ABI_VERSION 3   /* 2: td_step_io grew `obs_incremental` (+ reserved_) at its end; 3: td_set_option,
-                              config per handle, td_step_host as one graph launch */
+                              config per handle, td_step_host as one graph launch.  Added since, without a layout
+                              change: TD_OPT_GENERIC_KERNELS / HOST_CHAIN / HOST_FIRST_CHUNK / HOST_ZERO_COPY,
+                              td_alloc_compressible / td_free_compressible */
 
 enum { TD_OK = 0, TD_E_INVALID = -1, TD_E_CUDA = -2, TD_E_ALLOC = -3, TD_E_STATE = -4,
        TD_E_OVERFLOW = -5 };
