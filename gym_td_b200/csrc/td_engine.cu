@@ -780,9 +780,7 @@ extern "C" int td_observe_as(td_handle *h, int obs_format, void *obs_dev, void *
     return TD_OK;
 }
 
-// Host-buffer step.  Large batches are cut into chunks that alternate between two internal streams, so that
-// the host->device copy of chunk c+1 and the device->host copy of chunk c-1 overlap the kernel of chunk c
-// (instances are independent, so a chunk is a complete unit of work).
+// Compact snapshots: the env records as they are, and observations rebuilt from them later.
 extern "C" int td_snapshot(td_handle *h, void *records_out_dev, void *stream)
 {
     if (!h) return TD_E_INVALID;
@@ -816,11 +814,13 @@ extern "C" int td_observe_snapshot(td_handle *h, const void *records_dev, int n,
     return TD_OK;
 }
 
-// One host-buffer step as a list of operations: per chunk of envs the action copies (host -> device), the step
-// kernel, the output copies (device -> host).  The kernels run in chunk order; a chunk's input copy overlaps the
-// kernels before it and its output copy the kernels after it (instances are independent, so a chunk is a
-// complete unit of work).  The list is either instantiated once as a CUDA graph and replayed with one launch
-// (default), or issued on the stream call by call (TD_OPT_HOST_GRAPH = 0, pageable host memory).
+// One host-buffer step (td_step_host).  Inputs the step kernel can read from the caller's page-locked buffer
+// itself (small actions) and outputs it can store there itself (the packed record per env) need no copy at all: the
+// call is then one kernel launch and the synchronisation.  Whatever is left is a list of operations per chunk of
+// envs -- action copies (host -> device), the step kernel, output copies (device -> host); instances are
+// independent, so a chunk is a complete unit of work.  The list is instantiated once as a CUDA graph whose chunk
+// kernels are independent branches behind their own copies (or chained, TD_OPT_HOST_CHAIN) and replayed with one
+// launch, or issued on the stream call by call (TD_OPT_HOST_GRAPH = 0, pageable host memory).
 
 static void host_chunk_copies(const td_handle *h, const td_step_io *io, const td_host_io *host, size_t b, size_t n,
                               std::vector<HostCopy> &in, std::vector<HostCopy> &out)
