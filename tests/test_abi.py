@@ -104,6 +104,12 @@ def test_no_cpu_fallback():
     import gym_td_b200
     with pytest.raises(E.TdError):
         gym_td_b200.make("TD-def-small-v0", seed=1)
+    # the compressible-memory allocator is no exception: an error code and a message, no memory
+    ptr = C.c_void_p(0x1234)
+    assert E.lib().td_alloc_compressible(0, 1 << 20, C.byref(ptr), None) in (-2, -4) and not ptr.value
+    assert E.lib().td_last_error(None)
+    with pytest.raises(E.TdError):
+        E.CompressibleBuffer(1 << 20, 0)
 
 
 def _run_c_demo(tmp_path):
