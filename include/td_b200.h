@@ -310,8 +310,10 @@ int td_step_host(td_handle *h, const td_step_io *io, const td_host_io *host, voi
  * copies out), cached per distinct set of buffers; with pageable host memory, or TD_OPT_HOST_GRAPH = 0, the same
  * operations are issued on the stream one by one.  Large batches are cut automatically: the chunk kernels are
  * independent branches of the graph, each starts as soon as its own actions have arrived (the first chunk is short),
- * so the action copy hides behind the step.  Buffers of a cached graph must stay allocated (and page-locked) while
- * the handle lives.  Passing the legacy default stream (NULL) is fine. */
+ * so the action copy hides behind the step.  Small actions are not copied at all: the step kernel reads them from
+ * the page-locked host buffer (TD_OPT_HOST_ZERO_COPY), and io->def_action_dev / atk_action_dev, which only stage
+ * the copy, are then left untouched.  Buffers of a cached graph must stay allocated (and page-locked) while the
+ * handle lives.  Passing the legacy default stream (NULL) is fine. */
 
 /* tuning knobs of a handle (no environment variables are read anywhere in the library) */
 enum { TD_OPT_HOST_CHUNKS = 1,   /* td_step_host: chunks the batch is cut into; 0 = automatic (4 from 8,192 envs on) */
